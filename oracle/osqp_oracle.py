@@ -119,6 +119,17 @@ def _rowmax(M):
     return np.asarray(abs(M).max(axis=1).todense()).ravel()
 
 
+def _rowmax_reduceat(M):
+    """row-wise max |.| of a CSR matrix with sorted, possibly empty rows."""
+    ip = M.indptr
+    out = np.zeros(M.shape[0])
+    nz = np.diff(ip) > 0
+    if nz.any():
+        red = np.maximum.reduceat(np.abs(M.data), ip[:-1][nz])
+        out[nz] = red
+    return out
+
+
 def full_symmetric(P):
     """The facade sends triu(P) (interface.py:221-222); purepy wants the full matrix."""
     P = sp.csc_matrix(P)
@@ -175,27 +186,46 @@ class OracleSolver:
                                     solve_time=0.0, polish_time=0.0, cg_iters=0)
 
     def _ruiz(self, P, q, A, l, u):
-        """ref:389-497 (Ruiz equilibration + cost normalisation, `scaling` passes)."""
+        """ref:389-497 (Ruiz equilibration + cost normalisation, `scaling` passes).  Same arithmetic as
+        the reference's diag(s) @ M @ diag(s) products, done in place on the CSR value arrays so that the
+        n = m = 1e6 baseline problem scales in seconds."""
         n, m = self.n, self.m
+        P = sp.csr_matrix(P, dtype=float, copy=True)
+        A = sp.csr_matrix(A, dtype=float, copy=True)
+        P.sort_indices(); A.sort_indices()
+        At = sp.csr_matrix(A.T)                      # column norms of A = row norms of A'
+        At.sort_indices()
+        prow = np.repeat(np.arange(n), np.diff(P.indptr))
+        arow = np.repeat(np.arange(m), np.diff(A.indptr))
+        atrow = np.repeat(np.arange(n), np.diff(At.indptr))
+
+        def rowmax(M, rows):
+            out = np.zeros(M.shape[0])
+            if M.nnz:
+                np.maximum.at(out, rows, np.abs(M.data)) if M.nnz < 4096 else out.__setitem__(
+                    slice(None), _rowmax_reduceat(M))
+            return out
+
         D, E, c = np.ones(n), np.ones(m), 1.0
+        q, l, u = q.copy(), l.copy(), u.copy()
         for _ in range(int(self.s.scaling)):
-            # ref:348-361: column norms of the KKT matrix [[P, A'],[A, 0]]
-            colP = _rowmax(P.T.tocsr()) if P.nnz else np.zeros(n)
-            colA = _rowmax(sp.csr_matrix(A.T)) if m else np.zeros(n)
+            # ref:348-361: column norms of the KKT matrix [[P, A'],[A, 0]] (P symmetric: rows = columns)
+            colP = rowmax(P, prow)
+            colA = rowmax(At, atrow)
             sD = 1.0 / np.sqrt(_limit(np.maximum(colP, colA)))       # ref:419-421
-            sE = 1.0 / np.sqrt(_limit(_rowmax(A))) if m else np.zeros(0)
-            P = sp.csr_matrix(sp.diags(sD) @ P @ sp.diags(sD))       # ref:432-436
+            sE = 1.0 / np.sqrt(_limit(rowmax(A, arow))) if m else np.zeros(0)
+            P.data *= sD[prow] * sD[P.indices]                       # ref:432-436
             if m:
-                A = sp.csr_matrix(sp.diags(sE) @ A @ sp.diags(sD))
-            else:
-                A = sp.csr_matrix((0, n))
+                A.data *= sE[arow] * sD[A.indices]
+                At.data *= sD[atrow] * sE[At.indices]
             q, l, u = sD * q, sE * l, sE * u
             D, E = sD * D, sE * E                                    # ref:439-440
             # ref:443-448 cost normalisation
-            mean_colP = float(_rowmax(P.T.tocsr()).mean()) if P.nnz else 0.0
+            mean_colP = float(rowmax(P, prow).mean()) if P.nnz else 0.0
             qn = _limit(np.max(np.abs(q))) if n else 1.0
             ct = 1.0 / _limit(max(qn, mean_colP))
-            P, q, c = ct * P, ct * q, ct * c                         # ref:464-468
+            P.data *= ct
+            q, c = ct * q, ct * c                                    # ref:464-468
         self.D, self.E, self.c = D, E, c
         return P, q, A, l, u
 

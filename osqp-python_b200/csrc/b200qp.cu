@@ -1,0 +1,968 @@
+// b200qp.cu -- host driver + C ABI (include/b200qp.h) of the Blackwell-native OSQP ADMM engine.
+//
+// setup():   host CSC -> device CSR(P full), CSR(A), CSR(A') (+ position maps for value updates),
+//            Ruiz equilibration, rho vector, Jacobi diagonal, static row partitions  -- once.
+// solve():   ONE cooperative launch of the persistent ADMM kernel (admm_kernel.cuh); the host
+//            reads back a 128-byte result block, then x/y (or a certificate).
+// There is no CPU compute path: every numerical step of the reference's solve()/update()/
+// warm_start() runs in the kernels of this translation unit.
+#include "../../include/b200qp.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "admm_kernel.cuh"
+#include "aux_kernels.cuh"
+#include "spmv_kernels.cuh"
+
+using namespace b200qp;
+
+namespace {
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      std::fprintf(stderr, "[b200qp] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, \
+                   __LINE__, cudaGetErrorString(e_));                                              \
+      throw (int)B200QP_ALGEBRA_LOAD_ERROR;                                                        \
+    }                                                                                              \
+  } while (0)
+
+inline double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+template <class T>
+struct DBuf {                     // device array
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t cnt) {
+    free();
+    n = cnt;
+    CK(cudaMalloc(&p, std::max<size_t>(cnt, 1) * sizeof(T)));
+  }
+  void upload(const T* h, size_t cnt, cudaStream_t s) {
+    if (cnt) CK(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void zero(cudaStream_t s) { CK(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), s)); }
+  void free() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct DevCsr {
+  int rows = 0, cols = 0, nnz = 0;
+  DBuf<int> ptr, idx;
+  DBuf<double> val;
+  std::vector<int> h_ptr;         // host copy of the row pointers (partitioning)
+  void upload(int r, int c, const std::vector<int>& p, const std::vector<int>& i, const std::vector<double>& x,
+              cudaStream_t s) {
+    rows = r; cols = c; nnz = (int)x.size();
+    ptr.alloc(r + 1); idx.alloc(nnz + 8); val.alloc(nnz + 8);
+    idx.zero(s); val.zero(s);
+    ptr.upload(p.data(), r + 1, s); idx.upload(i.data(), nnz, s); val.upload(x.data(), nnz, s);
+    h_ptr = p;
+  }
+  CsrMat view() const { return CsrMat{rows, cols, nnz, ptr.p, idx.p, val.p}; }
+  void free() { ptr.free(); idx.free(); val.free(); }
+};
+
+const char* status_string(int s) {
+  switch (s) {
+    case B200QP_SOLVED: return "solved";
+    case B200QP_SOLVED_INACCURATE: return "solved inaccurate";
+    case B200QP_PRIMAL_INFEASIBLE: return "primal infeasible";
+    case B200QP_PRIMAL_INFEASIBLE_INACCURATE: return "primal infeasible inaccurate";
+    case B200QP_DUAL_INFEASIBLE: return "dual infeasible";
+    case B200QP_DUAL_INFEASIBLE_INACCURATE: return "dual infeasible inaccurate";
+    case B200QP_MAX_ITER_REACHED: return "maximum iterations reached";
+    case B200QP_TIME_LIMIT_REACHED: return "run time limit reached";
+    case B200QP_NON_CVX: return "problem non convex";
+    case B200QP_SIGINT: return "interrupted";
+    default: return "unsolved";
+  }
+}
+
+int validate_settings(const b200qp_settings* s, bool at_setup) {
+  if (!s) return B200QP_SETTINGS_VALIDATION_ERROR;
+  bool ok = s->rho > 0 && s->sigma > 0 && s->alpha > 0 && s->alpha < 2 && s->max_iter > 0 && s->eps_abs >= 0 &&
+            s->eps_rel >= 0 && (s->eps_abs > 0 || s->eps_rel > 0) && s->eps_prim_inf > 0 && s->eps_dual_inf > 0 &&
+            s->check_termination >= 0 && s->scaling >= 0 && s->delta > 0 && s->polish_refine_iter >= 0 &&
+            s->cg_max_iter > 0 && s->cg_tol_fraction > 0 && s->cg_tol_fraction < 1 && s->adaptive_rho_interval >= 0 &&
+            s->adaptive_rho_tolerance >= 1 && s->time_limit > 0 &&
+            (s->cg_precond == B200QP_NO_PRECONDITIONER || s->cg_precond == B200QP_DIAGONAL_PRECONDITIONER);
+  if (!ok) return B200QP_SETTINGS_VALIDATION_ERROR;
+  if (at_setup && s->linsys_solver != B200QP_INDIRECT_SOLVER) return B200QP_LINSYS_SOLVER_INIT_ERROR;
+  return 0;
+}
+
+struct Work {
+  int n = 0, m = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevCsr P, A, At;
+  // value-update maps
+  DBuf<int> mapA, Pt_colptr, Pt_rowidx, posU, posL;
+  int nnzPt = 0;
+  // n-vectors
+  DBuf<double> q, pdiag, D, Dinv, x, d, r, p, kp, px, Minv, tmp_n, tmp_n2;
+  // m-vectors
+  DBuf<double> l, u, E, Einv, z, y, ax, w2, w, rho_v, rho_inv, tmp_m;
+  DBuf<int> ctype;
+  // staging / outputs
+  DBuf<double> stage_d;          // max(n,m,nnz) doubles: H2D staging of caller arrays
+  DBuf<int> stage_i;
+  DBuf<double> sol_n, sol_m, cert_n, cert_m, scal;
+  DBuf<int> part_n, part_m;
+  DBuf<double> red;
+  DBuf<Ctrl> ctrl;
+  DBuf<KOut> out;
+  DBuf<LogRow> log;
+  int log_cap = 0;
+  double c = 1.0;
+  double nq_s = 0, nq_t = 0;
+  int G = 1, lgn = 8, lgm = 8, max_coop = 1;
+  bool first_run = true, clear_update_time = false;
+  b200qp_stats stats{};
+  double *h_x = nullptr, *h_y = nullptr, *h_pc = nullptr, *h_dc = nullptr;  // pinned
+  KOut h_out{};
+
+  ~Work() {
+    cudaSetDevice(device);
+    P.free(); A.free(); At.free();
+    mapA.free(); Pt_colptr.free(); Pt_rowidx.free(); posU.free(); posL.free();
+    for (DBuf<double>* b : {&q, &pdiag, &D, &Dinv, &x, &d, &r, &p, &kp, &px, &Minv, &tmp_n, &tmp_n2, &l, &u, &E, &Einv,
+                            &z, &y, &ax, &w2, &w, &rho_v, &rho_inv, &tmp_m, &stage_d, &sol_n, &sol_m, &cert_n, &cert_m,
+                            &scal, &red})
+      b->free();
+    ctype.free(); stage_i.free(); part_n.free(); part_m.free(); ctrl.free(); out.free(); log.free();
+    if (h_x) cudaFreeHost(h_x);
+    if (h_y) cudaFreeHost(h_y);
+    if (h_pc) cudaFreeHost(h_pc);
+    if (h_dc) cudaFreeHost(h_dc);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+inline Work* W(b200qp_solver* s) { return static_cast<Work*>(s->work); }
+inline const Work* W(const b200qp_solver* s) { return static_cast<const Work*>(s->work); }
+
+// ---- helpers ------------------------------------------------------------------------------------
+void launch_row_absmax(const DevCsr& M, double* out, cudaStream_t s) {
+  if (M.rows) k_row_absmax<<<cdiv((long long)M.rows * 8, 256), 256, 0, s>>>(M.view(), out);
+}
+void launch_scale(DevCsr& M, const double* rs, const double* cs, double scalar, cudaStream_t s) {
+  if (M.rows && M.nnz)
+    k_scale_csr<<<cdiv((long long)M.rows * 8, 256), 256, 0, s>>>(M.rows, M.ptr.p, M.idx.p, M.val.p, rs, cs, scalar);
+}
+
+void refresh_rho_and_precond(b200qp_solver* sv, bool retype) {
+  Work* w = W(sv);
+  const b200qp_settings* st = sv->settings;
+  if (w->m)
+    k_type_and_rho<<<cdiv(w->m, 256), 256, 0, w->stream>>>(w->m, w->l.p, w->u.p, st->rho, st->rho_is_vec, w->ctype.p,
+                                                           w->rho_v.p, w->rho_inv.p, retype ? 1 : 0);
+  k_jacobi<<<cdiv((long long)w->n * 8, 256), 256, 0, w->stream>>>(w->At.view(), w->pdiag.p, w->rho_v.p, st->sigma,
+                                                                 st->cg_precond == B200QP_DIAGONAL_PRECONDITIONER,
+                                                                 w->Minv.p);
+}
+
+// |q|inf in the scaled space and in the termination space
+void refresh_q_norms(b200qp_solver* sv) {
+  Work* w = W(sv);
+  double h[2];
+  k_absmax_sum<<<1, 1024, 0, w->stream>>>(w->n, w->q.p, nullptr, w->scal.p);
+  CK(cudaMemcpyAsync(h, w->scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  w->nq_s = h[0];
+  k_absmax_sum<<<1, 1024, 0, w->stream>>>(w->n, w->q.p, w->Dinv.p, w->scal.p);
+  CK(cudaMemcpyAsync(h, w->scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  w->nq_t = h[0];
+}
+
+// balanced contiguous row ranges: weight(row) = nnz of the row in each matrix + a constant
+void make_partition(int rows, int G, const std::vector<const std::vector<int>*>& ptrs, std::vector<int>& part) {
+  part.assign(G + 1, rows);
+  part[0] = 0;
+  if (rows == 0) { std::fill(part.begin(), part.end(), 0); return; }
+  auto wsum = [&](int r) {  // total weight of rows [0, r)
+    long long s = 8LL * r;
+    for (auto* p : ptrs) s += (*p)[r];
+    return s;
+  };
+  const long long total = wsum(rows);
+  int r = 0;
+  for (int g = 1; g < G; ++g) {
+    const long long target = total * g / G;
+    int lo = r, hi = rows;
+    while (lo < hi) { const int mid = (lo + hi) / 2; if (wsum(mid) < target) lo = mid + 1; else hi = mid; }
+    r = lo;
+    part[g] = r;
+  }
+  part[G] = rows;
+}
+
+int pick_lg(double avg) { return avg <= 6.0 ? 4 : (avg <= 24.0 ? 8 : 32); }
+
+typedef void (*admm_fn)(const KArgs);
+admm_fn pick_kernel(int lgn, int lgm) {
+#define CASE(a, b) if (lgn == a && lgm == b) return admm_kernel<a, b>;
+  CASE(4, 4) CASE(4, 8) CASE(4, 32) CASE(8, 4) CASE(8, 8) CASE(8, 32) CASE(32, 4) CASE(32, 8) CASE(32, 32)
+#undef CASE
+  return admm_kernel<8, 8>;
+}
+
+void set_info_defaults(b200qp_info* info) {
+  std::memset(info, 0, sizeof(*info));
+  std::snprintf(info->status, sizeof(info->status), "%s", "unsolved");
+  info->status_val = B200QP_UNSOLVED;
+}
+
+void begin_update_timer(b200qp_solver* sv) {   // reference: _osqp.py:1316-1321
+  Work* w = W(sv);
+  if (w->clear_update_time) { w->clear_update_time = false; sv->info->update_time = 0.0; }
+}
+
+// stage a caller (pageable host) array on the device; consumed before returning to the caller
+const double* stage_doubles(Work* w, const double* h, size_t cnt, size_t offset = 0) {
+  if (cnt) CK(cudaMemcpyAsync(w->stage_d.p + offset, h, cnt * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+  return w->stage_d.p + offset;
+}
+
+KArgs make_args(b200qp_solver* sv) {
+  Work* w = W(sv);
+  const b200qp_settings* st = sv->settings;
+  KArgs a{};
+  a.n = w->n; a.m = w->m; a.G = w->G;
+  a.P = w->P.view(); a.A = w->A.view(); a.At = w->At.view();
+  a.q = w->q.p; a.pdiag = w->pdiag.p; a.D = w->D.p; a.Dinv = w->Dinv.p;
+  a.x = w->x.p; a.d = w->d.p; a.r = w->r.p; a.p = w->p.p; a.kp = w->kp.p; a.px = w->px.p; a.Minv = w->Minv.p;
+  a.l = w->l.p; a.u = w->u.p; a.E = w->E.p; a.Einv = w->Einv.p; a.ctype = w->ctype.p;
+  a.z = w->z.p; a.y = w->y.p; a.ax = w->ax.p; a.w2 = w->w2.p; a.w = w->w.p; a.rho_v = w->rho_v.p; a.rho_inv = w->rho_inv.p;
+  a.part_n = w->part_n.p; a.part_m = w->part_m.p; a.red = w->red.p; a.ctrl = w->ctrl.p; a.out = w->out.p;
+  a.log = w->log.p; a.log_cap = w->log_cap;
+  a.sigma = st->sigma; a.alpha = st->alpha; a.rho = st->rho; a.eps_abs = st->eps_abs; a.eps_rel = st->eps_rel;
+  a.eps_pinf = st->eps_prim_inf; a.eps_dinf = st->eps_dual_inf; a.c = w->c; a.adapt_tol = st->adaptive_rho_tolerance;
+  a.cg_tol_frac = st->cg_tol_fraction;
+  a.unscale = (st->scaling && !st->scaled_termination) ? 1 : 0;
+  a.nq_s = w->nq_s; a.nq_t = a.unscale ? w->nq_t : w->nq_s;
+  a.time_limit_ns = st->time_limit * 1e9;
+  a.max_iter = st->max_iter; a.check_term = st->check_termination; a.adaptive_rho = st->adaptive_rho;
+  a.adapt_interval = st->adaptive_rho_interval > 0 ? st->adaptive_rho_interval : 50;
+  a.cg_max_iter = st->cg_max_iter; a.cg_precond = st->cg_precond == B200QP_DIAGONAL_PRECONDITIONER;
+  a.rho_is_vec = st->rho_is_vec; a.check_dualgap = st->check_dualgap; a.verbose = st->verbose;
+  a.polish_mode = 0;
+  return a;
+}
+
+// one launch of the persistent kernel; fills w->h_out and device-timed milliseconds
+void run_admm(b200qp_solver* sv, const KArgs& a, float* ms) {
+  Work* w = W(sv);
+  CK(cudaMemsetAsync(w->ctrl.p, 0, sizeof(Ctrl), w->stream));
+  CK(cudaMemsetAsync(w->out.p, 0, sizeof(KOut), w->stream));
+  admm_fn fn = pick_kernel(w->lgn, w->lgm);
+  void* params[] = {(void*)&a};
+  CK(cudaEventRecord(w->ev0, w->stream));
+  CK(cudaLaunchCooperativeKernel((const void*)fn, dim3(w->G), dim3(NT), params, 0, w->stream));
+  CK(cudaEventRecord(w->ev1, w->stream));
+  CK(cudaMemcpyAsync(&w->h_out, w->out.p, sizeof(KOut), cudaMemcpyDeviceToHost, w->stream));
+  CK(cudaStreamSynchronize(w->stream));
+  CK(cudaEventElapsedTime(ms, w->ev0, w->ev1));
+}
+
+// algorithmic HBM bytes of one solve (DESIGN.md "byte model"), from the kernel's own counters
+double algo_bytes(const Work* w, long long iters, long long cg, int check_every) {
+  const double n = w->n, m = w->m, zP = w->P.nnz, zA = w->A.nnz;
+  const double spP = 12 * zP + 4 * (n + 1), spA = 12 * zA + 4 * (m + 1), spAt = 12 * zA + 4 * (n + 1);
+  const double R = spP + spAt + 8 * n /*x*/ + 8 * m /*w2*/ + 8 * 2 * n /*q,Minv*/ + 8 * 2 * n /*r,p*/;
+  const double C1 = spA + 8 * n + 8 * m + 8 * m;
+  const double C2 = spP + spAt + 8 * n + 8 * m + 8 * n + 8 * n;
+  const double C3 = 8 * n * 7, C4 = 8 * n * 4;
+  const double Z = spA + 8 * n + 8 * m * 11 + 8 * n * 3;
+  const double chk = (check_every > 0) ? (double)(iters / check_every) * (12 * zA + 8 * m + 8 * 4 * n + 8 * 6 * m) : 0;
+  return (double)iters * (R + Z) + (double)cg * (C1 + C2 + C3 + C4) + chk;
+}
+
+}  // namespace
+
+static int polish_impl(b200qp_solver* solver);
+
+// ================================================================================ C ABI
+extern "C" {
+
+const char* b200qp_version(void) { return "0.1.0-b200"; }
+
+const char* b200qp_error_message(b200qp_int code) {
+  switch (code) {
+    case B200QP_NO_ERROR: return "no error";
+    case B200QP_DATA_VALIDATION_ERROR: return "problem data validation";
+    case B200QP_SETTINGS_VALIDATION_ERROR: return "solver settings validation";
+    case B200QP_LINSYS_SOLVER_INIT_ERROR: return "linear system solver not available (only the indirect PCG solver is)";
+    case B200QP_NONCVX_ERROR: return "problem non convex";
+    case B200QP_MEM_ALLOC_ERROR: return "memory allocation";
+    case B200QP_WORKSPACE_NOT_INIT_ERROR: return "solver workspace not initialized";
+    case B200QP_ALGEBRA_LOAD_ERROR: return "CUDA device / runtime not available";
+    case B200QP_FUNC_NOT_IMPLEMENTED: return "function not implemented";
+    default: return "unknown error";
+  }
+}
+
+b200qp_int b200qp_device_count(void) {
+  int nd = 0;
+  if (cudaGetDeviceCount(&nd) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return nd;
+}
+
+b200qp_int b200qp_capabilities(void) {
+  return B200QP_CAPABILITY_INDIRECT_SOLVER | B200QP_CAPABILITY_UPDATE_MATRICES;
+}
+
+void b200qp_set_default_settings(b200qp_settings* s) {
+  if (!s) return;
+  s->device = 0;
+  s->linsys_solver = B200QP_INDIRECT_SOLVER;
+  s->verbose = 1;
+  s->warm_starting = 1;
+  s->scaling = 10;
+  s->polishing = 0;
+  s->rho = 0.1;
+  s->rho_is_vec = 1;
+  s->sigma = 1e-6;
+  s->alpha = 1.6;
+  s->cg_max_iter = 100;
+  s->cg_tol_reduction = 10;
+  s->cg_tol_fraction = 0.15;
+  s->cg_precond = B200QP_DIAGONAL_PRECONDITIONER;
+  s->adaptive_rho = 1;
+  s->adaptive_rho_interval = 50;
+  s->adaptive_rho_fraction = 0.4;
+  s->adaptive_rho_tolerance = 5.0;
+  s->max_iter = 4000;
+  s->eps_abs = 1e-3;
+  s->eps_rel = 1e-3;
+  s->eps_prim_inf = 1e-4;
+  s->eps_dual_inf = 1e-4;
+  s->scaled_termination = 0;
+  s->check_termination = 25;
+  s->check_dualgap = 0;
+  s->time_limit = 1e10;
+  s->delta = 1e-6;
+  s->polish_refine_iter = 3;
+}
+
+b200qp_int b200qp_cleanup(b200qp_solver* solver) {
+  if (!solver) return 0;
+  delete W(solver);
+  delete solver->settings;
+  delete solver->solution;
+  delete solver->info;
+  delete solver;
+  return 0;
+}
+
+b200qp_int b200qp_setup(b200qp_solver** solverp, const b200qp_csc* P, const b200qp_float* q, const b200qp_csc* A,
+                        const b200qp_float* l, const b200qp_float* u, b200qp_int m, b200qp_int n,
+                        const b200qp_settings* settings) {
+  if (!solverp) return B200QP_DATA_VALIDATION_ERROR;
+  *solverp = nullptr;
+  const double t0 = now_s();
+  // ---- validation (reference: upstream validate_data / validate_settings; errors surface as
+  //      py::value_error(code), src/bindings.cpp.in:154-156)
+  int err = validate_settings(settings, true);
+  if (err) return err;
+  if (!P || !A || !q || n <= 0 || m < 0 || P->m != n || P->n != n || A->n != n || A->m != m) return B200QP_DATA_VALIDATION_ERROR;
+  if (m > 0 && (!l || !u)) return B200QP_DATA_VALIDATION_ERROR;
+  for (int i = 0; i < m; ++i)
+    if (!(l[i] <= u[i])) return B200QP_DATA_VALIDATION_ERROR;
+  const int nnzPt = P->p[n], nnzA = A->p[n];
+  for (int j = 0; j < n; ++j) {
+    for (int k = P->p[j]; k < P->p[j + 1]; ++k)
+      if (P->i[k] > j || P->i[k] < 0) return B200QP_DATA_VALIDATION_ERROR;   // must be upper triangular
+    for (int k = A->p[j]; k < A->p[j + 1]; ++k)
+      if (A->i[k] < 0 || A->i[k] >= m) return B200QP_DATA_VALIDATION_ERROR;
+  }
+  int nd = 0;
+  if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0 || settings->device < 0 || settings->device >= nd) {
+    cudaGetLastError();
+    return B200QP_ALGEBRA_LOAD_ERROR;   // no CUDA device: fail loudly, there is no CPU path
+  }
+
+  b200qp_solver* sv = new b200qp_solver();
+  sv->settings = new b200qp_settings(*settings);
+  sv->solution = new b200qp_solution();
+  sv->info = new b200qp_info();
+  set_info_defaults(sv->info);
+  Work* w = new Work();
+  sv->work = w;
+  sv->settings->rho = std::min(std::max(settings->rho, RHO_MIN), RHO_MAX);
+  try {
+    w->n = n; w->m = m; w->device = settings->device;
+    CK(cudaSetDevice(w->device));
+    int coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, w->device));
+    if (!coop) throw (int)B200QP_ALGEBRA_LOAD_ERROR;
+    CK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&w->ev0));
+    CK(cudaEventCreate(&w->ev1));
+    cudaStream_t s = w->stream;
+
+    // ---- host-side format conversion (once): triu CSC -> full CSR; CSC(A) -> CSR(A); A' = CSC(A) as-is
+    std::vector<int> Pp(n + 1, 0), Pj, posU(nnzPt), posL(nnzPt);
+    std::vector<double> Px, pdiag(n, 0.0);
+    {
+      for (int j = 0; j < n; ++j)
+        for (int k = P->p[j]; k < P->p[j + 1]; ++k) { Pp[P->i[k] + 1]++; if (P->i[k] != j) Pp[j + 1]++; }
+      for (int i = 0; i < n; ++i) Pp[i + 1] += Pp[i];
+      Pj.resize(Pp[n]); Px.resize(Pp[n]);
+      std::vector<int> fill(Pp.begin(), Pp.end() - 1);
+      for (int j = 0; j < n; ++j)
+        for (int k = P->p[j]; k < P->p[j + 1]; ++k) {
+          const int i = P->i[k];
+          if (i != j) { posL[k] = fill[j]; Pj[fill[j]] = i; Px[fill[j]++] = P->x[k]; }     // (j,i), i<j
+          else { posL[k] = -1; pdiag[i] += P->x[k]; }
+          posU[k] = fill[i]; Pj[fill[i]] = j; Px[fill[i]++] = P->x[k];                      // (i,j)
+        }
+    }
+    std::vector<int> Ap(m + 1, 0), Aj(nnzA), mapA(nnzA);
+    std::vector<double> Ax(nnzA);
+    {
+      for (int k = 0; k < nnzA; ++k) Ap[A->i[k] + 1]++;
+      for (int i = 0; i < m; ++i) Ap[i + 1] += Ap[i];
+      std::vector<int> fill(Ap.begin(), Ap.end() - 1);
+      for (int j = 0; j < n; ++j)
+        for (int k = A->p[j]; k < A->p[j + 1]; ++k) {
+          const int pos = fill[A->i[k]]++;
+          Aj[pos] = j; Ax[pos] = A->x[k]; mapA[k] = pos;
+        }
+    }
+    std::vector<int> Atp(A->p, A->p + n + 1), Ati(A->i, A->i + nnzA);
+    std::vector<double> Atx(A->x, A->x + nnzA);
+    w->P.upload(n, n, Pp, Pj, Px, s);
+    w->A.upload(m, n, Ap, Aj, Ax, s);
+    w->At.upload(n, m, Atp, Ati, Atx, s);
+    w->nnzPt = nnzPt;
+    w->mapA.alloc(nnzA); w->mapA.upload(mapA.data(), nnzA, s);
+    w->Pt_colptr.alloc(n + 1); w->Pt_colptr.upload(P->p, n + 1, s);
+    w->Pt_rowidx.alloc(nnzPt); w->Pt_rowidx.upload(P->i, nnzPt, s);
+    w->posU.alloc(nnzPt); w->posU.upload(posU.data(), nnzPt, s);
+    w->posL.alloc(nnzPt); w->posL.upload(posL.data(), nnzPt, s);
+
+    for (DBuf<double>* b : {&w->q, &w->pdiag, &w->D, &w->Dinv, &w->x, &w->d, &w->r, &w->p, &w->kp, &w->px, &w->Minv,
+                            &w->tmp_n, &w->tmp_n2, &w->sol_n, &w->cert_n}) { b->alloc(n); b->zero(s); }
+    for (DBuf<double>* b : {&w->l, &w->u, &w->E, &w->Einv, &w->z, &w->y, &w->ax, &w->w2, &w->w, &w->rho_v, &w->rho_inv,
+                            &w->tmp_m, &w->sol_m, &w->cert_m}) { b->alloc(m); b->zero(s); }
+    w->ctype.alloc(m); w->ctype.zero(s);
+    w->scal.alloc(8);
+    const size_t stage_len = std::max<size_t>(std::max<size_t>(n + 2 * (size_t)m, (size_t)nnzA), (size_t)nnzPt) + 8;
+    w->stage_d.alloc(stage_len);
+    w->stage_i.alloc(std::max(nnzA, nnzPt) + 8);
+    w->q.upload(q, n, s); w->pdiag.upload(pdiag.data(), n, s);
+    w->l.upload(l, m, s); w->u.upload(u, m, s);
+    k_vec_fill<<<cdiv(n, 256), 256, 0, s>>>(n, w->D.p, 1.0);
+    if (m) k_vec_fill<<<cdiv(m, 256), 256, 0, s>>>(m, w->E.p, 1.0);
+
+    // ---- Ruiz equilibration on device (reference: _osqp.py:389-497)
+    w->c = 1.0;
+    for (int it = 0; it < settings->scaling; ++it) {
+      launch_row_absmax(w->P, w->tmp_n.p, s);                 // = column norms (P symmetric)
+      launch_row_absmax(w->At, w->tmp_n2.p, s);               // column norms of A
+      if (!w->P.nnz) CK(cudaMemsetAsync(w->tmp_n.p, 0, n * sizeof(double), s));
+      k_ruiz_factor<<<cdiv(n, 256), 256, 0, s>>>(n, w->tmp_n.p, m ? w->tmp_n2.p : nullptr, w->tmp_n.p, w->D.p);
+      if (m) {
+        launch_row_absmax(w->A, w->tmp_m.p, s);
+        k_ruiz_factor<<<cdiv(m, 256), 256, 0, s>>>(m, w->tmp_m.p, nullptr, w->tmp_m.p, w->E.p);
+      }
+      // tmp_n = sD, tmp_m = sE
+      launch_scale(w->P, w->tmp_n.p, w->tmp_n.p, 1.0, s);
+      launch_scale(w->A, w->tmp_m.p, w->tmp_n.p, 1.0, s);
+      launch_scale(w->At, w->tmp_n.p, w->tmp_m.p, 1.0, s);
+      k_vec_mul<<<cdiv(n, 256), 256, 0, s>>>(n, w->q.p, w->tmp_n.p, 1.0);
+      k_vec_mul<<<cdiv(n, 256), 256, 0, s>>>(n, w->pdiag.p, w->tmp_n.p, 1.0);
+      k_vec_mul<<<cdiv(n, 256), 256, 0, s>>>(n, w->pdiag.p, w->tmp_n.p, 1.0);
+      // cost normalisation (_osqp.py:443-468): mean column norm of P vs |q|inf
+      double hq[2], hp[2] = {0, 0};
+      if (w->P.nnz) {
+        launch_row_absmax(w->P, w->tmp_n2.p, s);
+        k_absmax_sum<<<1, 1024, 0, s>>>(n, w->tmp_n2.p, nullptr, w->scal.p);
+        CK(cudaMemcpyAsync(hp, w->scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+      }
+      k_absmax_sum<<<1, 1024, 0, s>>>(n, w->q.p, nullptr, w->scal.p + 2);
+      CK(cudaMemcpyAsync(hq, w->scal.p + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      auto lim = [](double v) { return v < MIN_SCALING ? 1.0 : (v > MAX_SCALING ? MAX_SCALING : v); };
+      const double ct = 1.0 / lim(std::max(lim(hq[0]), hp[1] / n));
+      launch_scale(w->P, nullptr, nullptr, ct, s);
+      k_vec_mul<<<cdiv(n, 256), 256, 0, s>>>(n, w->q.p, nullptr, ct);
+      k_vec_mul<<<cdiv(n, 256), 256, 0, s>>>(n, w->pdiag.p, nullptr, ct);
+      w->c *= ct;
+    }
+    k_vec_recip<<<cdiv(n, 256), 256, 0, s>>>(n, w->Dinv.p, w->D.p);
+    if (m) {
+      k_vec_recip<<<cdiv(m, 256), 256, 0, s>>>(m, w->Einv.p, w->E.p);
+      k_vec_mul<<<cdiv(m, 256), 256, 0, s>>>(m, w->l.p, w->E.p, 1.0);
+      k_vec_mul<<<cdiv(m, 256), 256, 0, s>>>(m, w->u.p, w->E.p, 1.0);
+    }
+    refresh_q_norms(sv);
+    refresh_rho_and_precond(sv, true);
+
+    // ---- launch geometry + static partitions
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, w->device));
+    w->lgn = pick_lg(n ? (double)(w->P.nnz + w->At.nnz) / n : 1.0);
+    w->lgm = pick_lg(m ? (double)w->A.nnz / m : 1.0);
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)pick_kernel(w->lgn, w->lgm), NT, 0));
+    if (occ < 1) throw (int)B200QP_ALGEBRA_LOAD_ERROR;
+    w->max_coop = occ * prop.multiProcessorCount;
+    const long long work = (long long)w->P.nnz + 2LL * w->A.nnz + 4LL * (n + m);
+    long long want = work / 8192;
+    if (const char* e = std::getenv("B200QP_GRID")) want = std::atoll(e);
+    w->G = (int)std::min<long long>(std::max<long long>(want, 1), w->max_coop);
+    std::vector<int> pn, pm;
+    make_partition(n, w->G, {&w->P.h_ptr, &w->At.h_ptr}, pn);
+    make_partition(m, w->G, {&w->A.h_ptr}, pm);
+    w->part_n.alloc(w->G + 1); w->part_n.upload(pn.data(), w->G + 1, s);
+    w->part_m.alloc(w->G + 1); w->part_m.upload(pm.data(), w->G + 1, s);
+    w->red.alloc((size_t)2 * KMAX * w->G); w->red.zero(s);
+    w->ctrl.alloc(1); w->out.alloc(1);
+    w->log_cap = 4096;
+    w->log.alloc(w->log_cap);
+    CK(cudaMallocHost(&w->h_x, std::max(n, 1) * sizeof(double)));
+    CK(cudaMallocHost(&w->h_y, std::max(m, 1) * sizeof(double)));
+    CK(cudaMallocHost(&w->h_pc, std::max(m, 1) * sizeof(double)));
+    CK(cudaMallocHost(&w->h_dc, std::max(n, 1) * sizeof(double)));
+    std::fill(w->h_x, w->h_x + n, 0.0); std::fill(w->h_dc, w->h_dc + n, 0.0);
+    std::fill(w->h_y, w->h_y + m, 0.0); std::fill(w->h_pc, w->h_pc + m, 0.0);
+    sv->solution->x = w->h_x; sv->solution->y = w->h_y;
+    sv->solution->prim_inf_cert = w->h_pc; sv->solution->dual_inf_cert = w->h_dc;
+    CK(cudaStreamSynchronize(s));
+    w->stats.n = n; w->stats.m = m; w->stats.nnzP_full = w->P.nnz; w->stats.nnzA = w->A.nnz;
+    w->stats.grid = w->G; w->stats.block = NT;
+  } catch (int code) {
+    b200qp_cleanup(sv);
+    return code;
+  } catch (const std::bad_alloc&) {
+    b200qp_cleanup(sv);
+    return B200QP_MEM_ALLOC_ERROR;
+  }
+  sv->info->setup_time = now_s() - t0;
+  if (sv->settings->verbose) {
+    std::printf("-----------------------------------------------------------------\n"
+                "  b200qp %s  -  OSQP ADMM on Blackwell (persistent fp64 CUDA kernel)\n"
+                "-----------------------------------------------------------------\n"
+                "problem:  variables n = %d, constraints m = %d, nnz(P) + nnz(A) = %d\n"
+                "settings: indirect PCG (cg_max_iter %d, tol fraction %.2g), eps_abs = %.1e, eps_rel = %.1e,\n"
+                "          rho = %.2e%s, sigma = %.1e, alpha = %.2f, max_iter = %d, scaling %d, grid %d x %d\n\n",
+                b200qp_version(), n, m, nnzPt + nnzA, sv->settings->cg_max_iter, sv->settings->cg_tol_fraction,
+                sv->settings->eps_abs, sv->settings->eps_rel, sv->settings->rho,
+                sv->settings->adaptive_rho ? " (adaptive)" : "", sv->settings->sigma, sv->settings->alpha,
+                sv->settings->max_iter, sv->settings->scaling, W(sv)->G, NT);
+    std::fflush(stdout);
+  }
+  *solverp = sv;
+  return 0;
+}
+
+void b200qp_cold_start(b200qp_solver* solver) {
+  if (!solver || !solver->work) return;
+  Work* w = W(solver);
+  cudaSetDevice(w->device);
+  w->x.zero(w->stream); w->z.zero(w->stream); w->y.zero(w->stream);
+}
+
+b200qp_int b200qp_solve(b200qp_solver* solver) {
+  if (!solver || !solver->work) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  Work* w = W(solver);
+  b200qp_settings* st = solver->settings;
+  b200qp_info* info = solver->info;
+  const double t0 = now_s();
+  try {
+    CK(cudaSetDevice(w->device));
+    if (w->clear_update_time) info->update_time = 0.0;
+    if (!st->warm_starting) b200qp_cold_start(solver);      // reference: _osqp.py:1203-1205
+    KArgs a = make_args(solver);
+    float ms = 0.f;
+    run_admm(solver, a, &ms);
+    const KOut& o = w->h_out;
+    if (o.aborted || o.status == 0) {
+      std::fprintf(stderr, "[b200qp] ADMM kernel aborted (grid barrier watchdog)\n");
+      return B200QP_WORKSPACE_NOT_INIT_ERROR;
+    }
+    st->rho = o.rho;
+    info->iter = o.iter; info->status_val = o.status; info->rho_updates = o.rho_updates;
+    info->rho_estimate = o.rho_estimate; info->obj_val = o.obj; info->dual_obj_val = o.dual_obj;
+    info->duality_gap = o.gap; info->prim_res = o.prim_res; info->dual_res = o.dual_res;
+    info->rel_kkt_error = o.rel_kkt; info->primdual_int = 0.0; info->status_polish = 0;
+    const double nanv = std::nan("");
+    if (o.status == B200QP_PRIMAL_INFEASIBLE || o.status == B200QP_PRIMAL_INFEASIBLE_INACCURATE) {
+      info->obj_val = B200QP_INFTY; info->dual_obj_val = B200QP_INFTY; info->duality_gap = nanv;
+    } else if (o.status == B200QP_DUAL_INFEASIBLE || o.status == B200QP_DUAL_INFEASIBLE_INACCURATE) {
+      info->obj_val = -B200QP_INFTY; info->dual_obj_val = -B200QP_INFTY; info->duality_gap = nanv;
+    } else if (o.status == B200QP_NON_CVX) {
+      info->obj_val = nanv; info->dual_obj_val = nanv; info->duality_gap = nanv;
+    }
+    std::snprintf(info->status, sizeof(info->status), "%s", status_string(o.status));
+    w->stats.admm_iters = o.iter; w->stats.cg_iters = o.cg_iters; w->stats.grid_barriers = o.barriers;
+    w->stats.kernel_ms = ms;
+    w->stats.algo_bytes = algo_bytes(w, o.iter, o.cg_iters, st->check_termination);
+    info->solve_time = now_s() - t0;
+
+    if (st->verbose) {
+      std::vector<LogRow> rows(std::min(o.log_rows, w->log_cap));
+      if (!rows.empty())
+        CK(cudaMemcpy(rows.data(), w->log.p, rows.size() * sizeof(LogRow), cudaMemcpyDeviceToHost));
+      std::printf("iter   objective    prim res   dual res   rho        time\n");
+      for (size_t i = 0; i < rows.size(); ++i)
+        if (i == 0 || i + 1 == rows.size() || rows[i].iter % 200 == 0)
+          std::printf("%4d  %11.4e   %8.2e   %8.2e   %8.2e  %8.2es\n", rows[i].iter, rows[i].obj, rows[i].prim_res,
+                      rows[i].dual_res, rows[i].rho, rows[i].t_ms * 1e-3);
+    }
+
+    // polish (reference: _osqp.py:1277-1281) -- see polish.cuh
+    info->polish_time = 0.0;
+    if (st->polishing && o.status == B200QP_SOLVED) {
+      const double tp = now_s();
+      polish_impl(solver);
+      info->polish_time = now_s() - tp;
+    }
+
+    // solution / certificates (reference: _osqp.py:1098-1115)
+    const int mode = (o.status == B200QP_PRIMAL_INFEASIBLE || o.status == B200QP_PRIMAL_INFEASIBLE_INACCURATE) ? 1
+                   : (o.status == B200QP_DUAL_INFEASIBLE || o.status == B200QP_DUAL_INFEASIBLE_INACCURATE) ? 2 : 0;
+    const int n = w->n, m = w->m;
+    k_store_n<<<cdiv(n, 256), 256, 0, w->stream>>>(n, mode, w->x.p, w->d.p, w->D.p, st->alpha, w->sol_n.p, w->cert_n.p);
+    CK(cudaMemcpyAsync(w->h_x, w->sol_n.p, n * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaMemcpyAsync(w->h_dc, w->cert_n.p, n * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    if (m) {
+      k_store_m<<<cdiv(m, 256), 256, 0, w->stream>>>(m, mode, w->y.p, w->w.p, w->E.p, 1.0 / w->c, w->sol_m.p, w->cert_m.p);
+      CK(cudaMemcpyAsync(w->h_y, w->sol_m.p, m * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+      CK(cudaMemcpyAsync(w->h_pc, w->cert_m.p, m * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    }
+    CK(cudaStreamSynchronize(w->stream));
+    info->run_time = (w->first_run ? info->setup_time : info->update_time) + info->solve_time + info->polish_time;
+    w->first_run = false;
+    w->clear_update_time = true;
+    if (st->verbose) {
+      std::printf("\nstatus:               %s\n", info->status);
+      if (st->polishing && o.status == B200QP_SOLVED)
+        std::printf("solution polish:      %s\n", info->status_polish == 1 ? "successful" : "unsuccessful");
+      std::printf("number of iterations: %d  (PCG iterations: %lld)\n", info->iter, (long long)o.cg_iters);
+      if (o.status == B200QP_SOLVED || o.status == B200QP_SOLVED_INACCURATE)
+        std::printf("optimal objective:    %.4f\n", info->obj_val);
+      std::printf("run time:             %.2es (ADMM kernel %.2es)\noptimal rho estimate: %.2e\n\n", info->run_time,
+                  ms * 1e-3, info->rho_estimate);
+      std::fflush(stdout);
+    }
+  } catch (int code) {
+    return code;
+  }
+  return 0;
+}
+
+b200qp_int b200qp_get_stats(const b200qp_solver* solver, b200qp_stats* stats) {
+  if (!solver || !solver->work || !stats) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  *stats = W(solver)->stats;
+  return 0;
+}
+
+b200qp_int b200qp_warm_start(b200qp_solver* solver, const b200qp_float* x, const b200qp_float* y) {
+  if (!solver || !solver->work) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  Work* w = W(solver);
+  try {
+    CK(cudaSetDevice(w->device));
+    solver->settings->warm_starting = 1;                    // reference: _osqp.py:1498
+    const int n = w->n, m = w->m;
+    const double* dx = x ? stage_doubles(w, x, n, 0) : nullptr;
+    const double* dy = (y && m) ? stage_doubles(w, y, m, n) : nullptr;
+    k_warm_x<<<cdiv(n, 256), 256, 0, w->stream>>>(n, dx, w->Dinv.p, w->x.p);
+    if (m) {
+      k_warm_y<<<cdiv(m, 256), 256, 0, w->stream>>>(m, dy, w->Einv.p, w->c, w->y.p);
+      k_spmv_simple<<<cdiv((long long)m * 8, 256), 256, 0, w->stream>>>(w->A.view(), w->x.p, w->z.p);  // z = A x
+    }
+    CK(cudaStreamSynchronize(w->stream));
+  } catch (int code) {
+    return code;
+  }
+  return 0;
+}
+
+b200qp_int b200qp_update_data_vec(b200qp_solver* solver, const b200qp_float* q_new, const b200qp_float* l_new,
+                                  const b200qp_float* u_new) {
+  if (!solver || !solver->work) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  Work* w = W(solver);
+  const double t0 = now_s();
+  begin_update_timer(solver);
+  try {
+    CK(cudaSetDevice(w->device));
+    const int n = w->n, m = w->m;
+    if (q_new) {                                            // q <- c D q   (reference: _osqp.py:1328)
+      const double* dq = stage_doubles(w, q_new, n, 0);
+      k_vec_set_mul<<<cdiv(n, 256), 256, 0, w->stream>>>(n, w->q.p, dq, w->D.p, w->c);
+      refresh_q_norms(solver);
+    }
+    if ((l_new || u_new) && m) {
+      // validate l <= u against the bounds that stay (reference: _osqp.py:1348, 1388, 1419)
+      std::vector<double> cur;
+      if (!l_new || !u_new) {
+        cur.resize(m);
+        k_vec_set_mul<<<cdiv(m, 256), 256, 0, w->stream>>>(m, w->tmp_m.p, l_new ? w->u.p : w->l.p, w->Einv.p, 1.0);
+        CK(cudaMemcpyAsync(cur.data(), w->tmp_m.p, m * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaStreamSynchronize(w->stream));
+      }
+      for (int i = 0; i < m; ++i) {
+        const double lo = l_new ? l_new[i] : cur[i], hi = u_new ? u_new[i] : cur[i];
+        if (!(lo <= hi + 1e-12 * std::fabs(hi))) return B200QP_DATA_VALIDATION_ERROR;
+      }
+      if (l_new) { const double* dl = stage_doubles(w, l_new, m, n);
+                   k_vec_set_mul<<<cdiv(m, 256), 256, 0, w->stream>>>(m, w->l.p, dl, w->E.p, 1.0); }
+      if (u_new) { const double* du = stage_doubles(w, u_new, m, n + m);
+                   k_vec_set_mul<<<cdiv(m, 256), 256, 0, w->stream>>>(m, w->u.p, du, w->E.p, 1.0); }
+      refresh_rho_and_precond(solver, true);                // constraint types may change (_osqp.py:526-562)
+    }
+    CK(cudaStreamSynchronize(w->stream));
+    solver->info->status_val = B200QP_UNSOLVED;
+    std::snprintf(solver->info->status, sizeof(solver->info->status), "%s", "unsolved");
+  } catch (int code) {
+    return code;
+  }
+  solver->info->update_time += now_s() - t0;
+  return 0;
+}
+
+b200qp_int b200qp_update_data_mat(b200qp_solver* solver, const b200qp_float* Px_new, const b200qp_int* Px_new_idx,
+                                  b200qp_int P_new_n, const b200qp_float* Ax_new, const b200qp_int* Ax_new_idx,
+                                  b200qp_int A_new_n) {
+  if (!solver || !solver->work) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  Work* w = W(solver);
+  const double t0 = now_s();
+  begin_update_timer(solver);
+  try {
+    CK(cudaSetDevice(w->device));
+    const int n = w->n;
+    if (Px_new) {
+      const int cnt = Px_new_idx ? P_new_n : w->nnzPt;
+      if (cnt < 0 || cnt > w->nnzPt || (!Px_new_idx && P_new_n && P_new_n != w->nnzPt)) return B200QP_DATA_VALIDATION_ERROR;
+      if (Px_new_idx)
+        for (int t = 0; t < cnt; ++t)
+          if (Px_new_idx[t] < 0 || Px_new_idx[t] >= w->nnzPt) return B200QP_DATA_VALIDATION_ERROR;
+      if (cnt) {
+        const double* dv = stage_doubles(w, Px_new, cnt, 0);
+        const int* di = nullptr;
+        if (Px_new_idx) { CK(cudaMemcpyAsync(w->stage_i.p, Px_new_idx, cnt * sizeof(int), cudaMemcpyHostToDevice, w->stream)); di = w->stage_i.p; }
+        k_update_P<<<cdiv(cnt, 256), 256, 0, w->stream>>>(cnt, dv, di, w->Pt_colptr.p, w->Pt_rowidx.p, n, w->posU.p, w->posL.p,
+                                                          w->D.p, w->c, w->P.val.p, w->pdiag.p);
+        CK(cudaStreamSynchronize(w->stream));
+      }
+    }
+    if (Ax_new) {
+      const int nnzA = w->A.nnz;
+      const int cnt = Ax_new_idx ? A_new_n : nnzA;
+      if (cnt < 0 || cnt > nnzA || (!Ax_new_idx && A_new_n && A_new_n != nnzA)) return B200QP_DATA_VALIDATION_ERROR;
+      if (Ax_new_idx)
+        for (int t = 0; t < cnt; ++t)
+          if (Ax_new_idx[t] < 0 || Ax_new_idx[t] >= nnzA) return B200QP_DATA_VALIDATION_ERROR;
+      if (cnt) {
+        const double* dv = stage_doubles(w, Ax_new, cnt, 0);
+        const int* di = nullptr;
+        if (Ax_new_idx) { CK(cudaMemcpyAsync(w->stage_i.p, Ax_new_idx, cnt * sizeof(int), cudaMemcpyHostToDevice, w->stream)); di = w->stage_i.p; }
+        k_update_A<<<cdiv(cnt, 256), 256, 0, w->stream>>>(cnt, dv, di, w->At.ptr.p, w->At.idx.p, n, w->mapA.p, w->D.p, w->E.p,
+                                                          w->At.val.p, w->A.val.p);
+      }
+    }
+    refresh_rho_and_precond(solver, false);                 // Jacobi diagonal follows P and A
+    CK(cudaStreamSynchronize(w->stream));
+    solver->info->status_val = B200QP_UNSOLVED;
+    std::snprintf(solver->info->status, sizeof(solver->info->status), "%s", "unsolved");
+  } catch (int code) {
+    return code;
+  }
+  solver->info->update_time += now_s() - t0;
+  return 0;
+}
+
+b200qp_int b200qp_update_rho(b200qp_solver* solver, b200qp_float rho_new) {
+  if (!solver || !solver->work) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  if (!(rho_new > 0)) return B200QP_SETTINGS_VALIDATION_ERROR;   // reference: _osqp.py:1583
+  Work* w = W(solver);
+  try {
+    CK(cudaSetDevice(w->device));
+    solver->settings->rho = std::min(std::max(rho_new, RHO_MIN), RHO_MAX);
+    refresh_rho_and_precond(solver, false);
+    CK(cudaStreamSynchronize(w->stream));
+  } catch (int code) {
+    return code;
+  }
+  return 0;
+}
+
+b200qp_int b200qp_update_settings(b200qp_solver* solver, const b200qp_settings* ns) {
+  if (!solver || !solver->work) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  b200qp_settings* st = solver->settings;
+  // fields fixed at setup keep their value (scaling, sigma, device, linsys_solver, rho_is_vec);
+  // rho goes through b200qp_update_rho (interface.py:299-300)
+  b200qp_settings t = *ns;
+  t.device = st->device; t.linsys_solver = st->linsys_solver; t.scaling = st->scaling; t.sigma = st->sigma;
+  t.rho_is_vec = st->rho_is_vec; t.rho = st->rho;
+  const int err = validate_settings(&t, false);
+  if (err) return err;
+  const bool precond_changed = t.cg_precond != st->cg_precond;
+  *st = t;
+  if (precond_changed) return b200qp_update_rho(solver, st->rho);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------- standalone SpMV
+struct b200qp_spmv_plan {
+  int device = 0;
+  DevCsr M;
+  DBuf<int> tiles;
+  int T = 0;
+  DBuf<double> x, y;
+  DBuf<char> flush;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int sms = 148;
+};
+
+b200qp_int b200qp_spmv_num_variants(void) { return 3; }
+const char* b200qp_spmv_variant_name(b200qp_int v) {
+  return v == 0 ? "group" : v == 1 ? "stream-tma" : v == 2 ? "scalar" : "?";
+}
+
+static void make_tiles(const std::vector<int>& ptr, int rows, std::vector<int>& tiles) {
+  tiles.clear();
+  int r = 0;
+  while (r < rows) {
+    tiles.push_back(r);
+    int e = r + 1;   // at least one row (a single long row becomes its own tile)
+    while (e < rows && e - r < ST_NT && ptr[e + 1] - ptr[r] <= ST_TILE) ++e;
+    if (ptr[e] - ptr[r] > ST_TILE) e = r + 1;
+    r = e;
+  }
+  tiles.push_back(rows);
+}
+
+b200qp_int b200qp_spmv_plan_create(b200qp_spmv_plan** planp, b200qp_int rows, b200qp_int cols, const b200qp_int* ptr,
+                                   const b200qp_int* idx, const b200qp_float* val, b200qp_int device) {
+  if (!planp || rows < 0 || cols <= 0 || !ptr) return B200QP_DATA_VALIDATION_ERROR;
+  if (b200qp_device_count() <= device) return B200QP_ALGEBRA_LOAD_ERROR;
+  b200qp_spmv_plan* pl = new b200qp_spmv_plan();
+  try {
+    pl->device = device;
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&pl->e0));
+    CK(cudaEventCreate(&pl->e1));
+    const int nnz = ptr[rows];
+    std::vector<int> p(ptr, ptr + rows + 1), i(idx, idx + nnz);
+    std::vector<double> v(val, val + nnz);
+    pl->M.upload(rows, cols, p, i, v, pl->stream);
+    std::vector<int> tiles;
+    make_tiles(p, rows, tiles);
+    pl->T = (int)tiles.size() - 1;
+    pl->tiles.alloc(tiles.size());
+    pl->tiles.upload(tiles.data(), tiles.size(), pl->stream);
+    pl->x.alloc(cols); pl->y.alloc(rows);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    pl->sms = prop.multiProcessorCount;
+    CK(cudaFuncSetAttribute(k_spmv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+    CK(cudaStreamSynchronize(pl->stream));
+  } catch (int code) {
+    delete pl;
+    return code;
+  }
+  *planp = pl;
+  return 0;
+}
+
+static void spmv_launch(b200qp_spmv_plan* pl, int variant) {
+  const CsrMat M = pl->M.view();
+  const int rows = M.rows;
+  if (!rows) return;
+  if (variant == 1) {
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_stream, ST_NT, ST_SMEM);
+    const int grid = std::max(1, std::min(pl->T, pl->sms * std::max(occ, 1)));
+    k_spmv_stream<<<grid, ST_NT, ST_SMEM, pl->stream>>>(M, pl->tiles.p, pl->T, pl->x.p, pl->y.p);
+  } else if (variant == 2) {
+    k_spmv_scalar<<<cdiv(rows, 256), 256, 0, pl->stream>>>(M, pl->x.p, pl->y.p);
+  } else {
+    const int lg = pick_lg(rows ? (double)M.nnz / rows : 1.0);
+    const int grid = cdiv((long long)rows * lg, 256);
+    if (lg == 4) k_spmv_group<4><<<grid, 256, 0, pl->stream>>>(M, pl->x.p, pl->y.p);
+    else if (lg == 8) k_spmv_group<8><<<grid, 256, 0, pl->stream>>>(M, pl->x.p, pl->y.p);
+    else k_spmv_group<32><<<grid, 256, 0, pl->stream>>>(M, pl->x.p, pl->y.p);
+  }
+}
+
+b200qp_int b200qp_spmv_plan_run(b200qp_spmv_plan* pl, const b200qp_float* x_host, b200qp_float* y_host,
+                                b200qp_int variant, b200qp_int reps, b200qp_int flush_l2, double* avg_ms) {
+  if (!pl) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  if (variant < 0 || variant >= b200qp_spmv_num_variants()) return B200QP_DATA_VALIDATION_ERROR;
+  try {
+    CK(cudaSetDevice(pl->device));
+    if (x_host) pl->x.upload(x_host, pl->M.cols, pl->stream);
+    const size_t FL = (size_t)512 << 20;
+    if (flush_l2 && !pl->flush.p) pl->flush.alloc(FL);
+    double total = 0.0;
+    reps = std::max(reps, 1);
+    for (int r = 0; r < reps; ++r) {
+      if (flush_l2) CK(cudaMemsetAsync(pl->flush.p, r & 0xff, FL, pl->stream));
+      CK(cudaEventRecord(pl->e0, pl->stream));
+      spmv_launch(pl, variant);
+      CK(cudaEventRecord(pl->e1, pl->stream));
+      CK(cudaStreamSynchronize(pl->stream));
+      CK(cudaGetLastError());
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, pl->e0, pl->e1));
+      total += ms;
+    }
+    if (avg_ms) *avg_ms = total / reps;
+    if (y_host && pl->M.rows) CK(cudaMemcpy(y_host, pl->y.p, pl->M.rows * sizeof(double), cudaMemcpyDeviceToHost));
+  } catch (int code) {
+    return code;
+  }
+  return 0;
+}
+
+void b200qp_spmv_plan_destroy(b200qp_spmv_plan* pl) {
+  if (!pl) return;
+  cudaSetDevice(pl->device);
+  pl->M.free(); pl->tiles.free(); pl->x.free(); pl->y.free(); pl->flush.free();
+  if (pl->e0) cudaEventDestroy(pl->e0);
+  if (pl->e1) cudaEventDestroy(pl->e1);
+  if (pl->stream) cudaStreamDestroy(pl->stream);
+  delete pl;
+}
+
+b200qp_int b200qp_spmv_csr_host(b200qp_int rows, b200qp_int cols, const b200qp_int* ptr, const b200qp_int* idx,
+                                const b200qp_float* val, const b200qp_float* x, b200qp_float* y, b200qp_int variant) {
+  b200qp_spmv_plan* pl = nullptr;
+  int err = b200qp_spmv_plan_create(&pl, rows, cols, ptr, idx, val, 0);
+  if (err) return err;
+  err = b200qp_spmv_plan_run(pl, x, y, variant, 1, 0, nullptr);
+  b200qp_spmv_plan_destroy(pl);
+  return err;
+}
+
+}  // extern "C"
+
+// ---- polish: placeholder until polish.cuh lands (status_polish = 0: not performed) ------------------
+static int polish_impl(b200qp_solver* solver) {
+  solver->info->status_polish = 0;
+  return 0;
+}
