@@ -42,6 +42,7 @@ N_VARS = int(os.environ.get("B200QP_BENCH_N", 1_000_000))
 N_CONS = int(os.environ.get("B200QP_BENCH_M", N_VARS))
 NNZ_ROW = 10
 SEED = 3
+ENGINE_SPEC = dict(cg_max_iter=100, cg_tol_fraction=0.05, rho_eq_factor=10.0)   # the engine's defaults, for the CPU port
 SOLVE_KW = dict(eps_abs=1e-3, eps_rel=1e-3, max_iter=4000, warm_starting=False, polishing=False)
 
 
@@ -130,8 +131,8 @@ def run_reference(args):
     P, q, A, l, u = make_problem()
     kw = dict(SOLVE_KW)
     kw.pop("warm_starting"); kw.pop("polishing")
-    s = OracleSolver(P, q, A, l, u, linsys="indirect", cg_max_iter=100, warm_starting=1, check_termination=0,
-                     adaptive_rho=0, **kw)
+    s = OracleSolver(P, q, A, l, u, linsys="indirect", warm_starting=1, check_termination=0,
+                     adaptive_rho=0, **ENGINE_SPEC, **kw)
     cap_s = float(os.environ.get("B200QP_REF_BUDGET_S", 150))
     t_begin = time.perf_counter()
     s.s.max_iter = 1
@@ -166,7 +167,7 @@ def cpu_baseline_sample(P, q, A, l, u, budget_iters=3):
     kw = dict(SOLVE_KW)
     kw.pop("warm_starting"); kw.pop("polishing")
     kw["max_iter"] = budget_iters
-    s = OracleSolver(P, q, A, l, u, linsys="indirect", cg_max_iter=100, check_termination=0, adaptive_rho=0, **kw)
+    s = OracleSolver(P, q, A, l, u, linsys="indirect", check_termination=0, adaptive_rho=0, **ENGINE_SPEC, **kw)
     t0 = time.perf_counter()
     r = s.solve()
     dt = time.perf_counter() - t0

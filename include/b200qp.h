@@ -107,7 +107,7 @@ typedef struct {
   b200qp_float sigma;
   b200qp_float alpha;
   b200qp_int cg_max_iter;
-  b200qp_int cg_tol_reduction; /* accepted, unused: the tolerance rule is cg_tol_fraction * ||r0|| */
+  b200qp_int cg_tol_reduction; /* accepted, unused: the PCG stops at |r|inf <= cg_tol_fraction * |r0|inf */
   b200qp_float cg_tol_fraction;
   b200qp_int cg_precond;
   b200qp_int adaptive_rho;

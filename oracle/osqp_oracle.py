@@ -98,9 +98,12 @@ class Settings:
     polish_refine_iter: int = 3
     time_limit: float = 1e10
     # indirect mode (engine spec)
-    cg_max_iter: int = 20
-    cg_tol_fraction: float = 0.15
+    cg_max_iter: int = 100
+    cg_tol_fraction: float = 0.05
     cg_precond: int = 1
+    # rho on equality rows = rho_eq_factor * rho.  Reference constant: 1e3 (ref:27); the engine's
+    # PCG-friendly default is 10 -- pass rho_eq_factor=10 to mirror the engine.
+    rho_eq_factor: float = 1e3
 
 
 def _limit(v):
@@ -239,7 +242,7 @@ class OracleSolver:
             self.rho_vec = np.full(self.m, rho)
         else:
             self.ctype = np.where(eq, 1, np.where(loose, -1, 0))     # eq wins (ref:516-518 order)
-            self.rho_vec = np.where(eq, RHO_EQ_FACTOR * rho, np.where(loose, RHO_MIN, rho))
+            self.rho_vec = np.where(eq, self.s.rho_eq_factor * rho, np.where(loose, RHO_MIN, rho))
         self.rho_inv = 1.0 / self.rho_vec if self.m else np.zeros(0)
 
     def _refresh_linsys(self):
@@ -256,7 +259,7 @@ class OracleSolver:
         """ref:1579-1597."""
         self.s.rho = float(min(max(rho_new, RHO_MIN), RHO_MAX))
         if self.s.rho_is_vec:
-            self.rho_vec = np.where(self.ctype == 1, RHO_EQ_FACTOR * self.s.rho,
+            self.rho_vec = np.where(self.ctype == 1, self.s.rho_eq_factor * self.s.rho,
                                     np.where(self.ctype == -1, RHO_MIN, self.s.rho))
         else:
             self.rho_vec = np.full(self.m, self.s.rho)

@@ -46,6 +46,7 @@ struct KArgs {
   LogRow* log; int log_cap;
   // settings
   double sigma, alpha, rho, eps_abs, eps_rel, eps_pinf, eps_dinf, c, adapt_tol, cg_tol_frac;
+  double rho_eq_factor;       // rho on equality rows = rho_eq_factor * rho (reference: 1e3, _osqp.py:27)
   double nq_s, nq_t;          // |q|inf scaled, |Dinv q|inf (termination space)
   double time_limit_ns;
   int max_iter, check_term, adaptive_rho, adapt_interval, cg_max_iter, cg_precond;
@@ -92,9 +93,9 @@ __device__ __forceinline__ double row_dot_sq(const CsrMat& M, const double* xv, 
   return acc;
 }
 
-__device__ __forceinline__ double rho_of_type(int ct, double rho, int rho_is_vec) {
+__device__ __forceinline__ double rho_of_type(int ct, double rho, int rho_is_vec, double eq_factor) {
   if (!rho_is_vec) return rho;
-  return ct == 1 ? RHO_EQ_FACTOR * rho : (ct == -1 ? RHO_MIN : rho);
+  return ct == 1 ? eq_factor * rho : (ct == -1 ? RHO_MIN : rho);
 }
 
 #define B200QP_BARRIER_OR_DIE() do { if (!sync.barrier()) { if (blockIdx.x == 0 && threadIdx.x == 0) a.out->aborted = 1; return; } } while (0)
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
         rho = rho_new;
         rho_updates++;
         for (int i = m0 + tid; i < m1; i += NT) {
-          const double rv = rho_of_type(a.ctype[i], rho, a.rho_is_vec);
+          const double rv = rho_of_type(a.ctype[i], rho, a.rho_is_vec, a.rho_eq_factor);
           a.rho_v[i] = rv;
           a.rho_inv[i] = 1.0 / rv;
           a.w2[i] = rv * (a.z[i] - a.ax[i]) - a.y[i];

@@ -90,7 +90,7 @@ __global__ void k_absmax_sum(int len, const double* __restrict__ v, const double
 
 // ---- rho vector / constraint typing (reference: _osqp.py:499-562) -------------------------------
 __global__ void k_type_and_rho(int m, const double* __restrict__ l, const double* __restrict__ u, double rho,
-                               int rho_is_vec, int* __restrict__ ctype, double* __restrict__ rho_v,
+                               int rho_is_vec, double eq_factor, int* __restrict__ ctype, double* __restrict__ rho_v,
                                double* __restrict__ rho_inv, int retype) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < m) {
@@ -100,7 +100,7 @@ __global__ void k_type_and_rho(int m, const double* __restrict__ l, const double
       ct = (ui - li < RHO_TOL) ? 1 : ((li < -INF_THRESH && ui > INF_THRESH) ? -1 : 0);
       ctype[i] = ct;
     }
-    const double rv = rho_is_vec ? (ct == 1 ? RHO_EQ_FACTOR * rho : (ct == -1 ? RHO_MIN : rho)) : rho;
+    const double rv = rho_is_vec ? (ct == 1 ? eq_factor * rho : (ct == -1 ? RHO_MIN : rho)) : rho;
     rho_v[i] = rv;
     rho_inv[i] = 1.0 / rv;
   }
@@ -199,6 +199,53 @@ __global__ void k_store_m(int m, int mode, const double* __restrict__ y, const d
   const double nanv = __longlong_as_double(0x7ff8000000000000LL);
   out_y[i] = mode == 0 ? E[i] * y[i] * cinv : nanv;
   out_pcert[i] = mode == 1 ? E[i] * dyp[i] : nanv;
+}
+
+// ---- polish support (reference: _osqp.py:1710-1828) ------------------------------------------------
+// Active-set guess (ref:1719-1720) and the bounds / rho / duals of the equality-constrained problem the
+// persistent kernel is re-run on: active rows become equalities at the active bound, the others are
+// released (infinite bounds, rho = RHO_MIN, y = 0).
+__global__ void k_polish_prepare(int m, const double* __restrict__ l, const double* __restrict__ u,
+                                 const double* __restrict__ z, const double* __restrict__ ax, double rho_act,
+                                 double* __restrict__ y, double* __restrict__ zp, double* __restrict__ lp,
+                                 double* __restrict__ up, int* __restrict__ ctp, double* __restrict__ rho_v,
+                                 double* __restrict__ rho_inv, int* __restrict__ n_active) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double zi = z[i], yi = y[i], li = l[i], ui = u[i];
+  const bool low = (zi - li) < -yi, upp = (ui - zi) < yi;
+  if (low || upp) {
+    const double b = low ? li : ui;
+    lp[i] = b; up[i] = b; zp[i] = b; ctp[i] = 1;
+    rho_v[i] = rho_act; rho_inv[i] = 1.0 / rho_act;
+    atomicAdd(n_active, 1);
+  } else {
+    lp[i] = -QP_INFTY; up[i] = QP_INFTY; zp[i] = ax[i]; ctp[i] = -1;
+    rho_v[i] = RHO_MIN; rho_inv[i] = 1.0 / RHO_MIN;
+    y[i] = 0.0;
+  }
+}
+
+// (z, y) <- normal-cone projection of (A x + y) on the ORIGINAL box (ref:676-680); partial: |Einv (Ax - z)|inf
+__global__ void k_polish_normalcone(int m, const double* __restrict__ ax, const double* __restrict__ l,
+                                    const double* __restrict__ u, const double* __restrict__ Einv,
+                                    double* __restrict__ y, double* __restrict__ z, double* __restrict__ res) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double t = ax[i] + y[i];
+  const double zn = fmin(fmax(t, l[i]), u[i]);
+  z[i] = zn;
+  y[i] = t - zn;
+  res[i] = (Einv ? Einv[i] : 1.0) * (ax[i] - zn);
+}
+// dres = Dinv .* (px + q + aty) ; xq = x .* (0.5 px + q)
+__global__ void k_polish_dual(int n, const double* __restrict__ px, const double* __restrict__ q,
+                              const double* __restrict__ aty, const double* __restrict__ Dinv,
+                              const double* __restrict__ x, double* __restrict__ dres, double* __restrict__ xq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dres[i] = (Dinv ? Dinv[i] : 1.0) * (px[i] + q[i] + aty[i]);
+  xq[i] = x[i] * (0.5 * px[i] + q[i]);
 }
 
 }  // namespace b200qp

@@ -123,6 +123,9 @@ struct Work {
   DBuf<double> stage_d;          // max(n,m,nnz) doubles: H2D staging of caller arrays
   DBuf<int> stage_i;
   DBuf<double> sol_n, sol_m, cert_n, cert_m, scal;
+  // polish workspace (allocated on first use)
+  DBuf<double> pol_l, pol_u, pol_rho, pol_rhoinv, pol_Minv, bk_x, bk_z, bk_y, bk_ax;
+  DBuf<int> pol_ctype, pol_count;
   DBuf<int> part_n, part_m;
   DBuf<double> red;
   DBuf<Ctrl> ctrl;
@@ -130,6 +133,7 @@ struct Work {
   DBuf<LogRow> log;
   int log_cap = 0;
   double c = 1.0;
+  double rho_eq_factor = 10.0;   // engine default; reference uses 1e3; env B200QP_RHO_EQ_FACTOR
   double nq_s = 0, nq_t = 0;
   int G = 1, lgn = 8, lgm = 8, max_coop = 1;
   bool first_run = true, clear_update_time = false;
@@ -143,8 +147,9 @@ struct Work {
     mapA.free(); Pt_colptr.free(); Pt_rowidx.free(); posU.free(); posL.free();
     for (DBuf<double>* b : {&q, &pdiag, &D, &Dinv, &x, &d, &r, &p, &kp, &px, &Minv, &tmp_n, &tmp_n2, &l, &u, &E, &Einv,
                             &z, &y, &ax, &w2, &w, &rho_v, &rho_inv, &tmp_m, &stage_d, &sol_n, &sol_m, &cert_n, &cert_m,
-                            &scal, &red})
+                            &scal, &red, &pol_l, &pol_u, &pol_rho, &pol_rhoinv, &pol_Minv, &bk_x, &bk_z, &bk_y, &bk_ax})
       b->free();
+    pol_ctype.free(); pol_count.free();
     ctype.free(); stage_i.free(); part_n.free(); part_m.free(); ctrl.free(); out.free(); log.free();
     if (h_x) cudaFreeHost(h_x);
     if (h_y) cudaFreeHost(h_y);
@@ -172,7 +177,7 @@ void refresh_rho_and_precond(b200qp_solver* sv, bool retype) {
   Work* w = W(sv);
   const b200qp_settings* st = sv->settings;
   if (w->m)
-    k_type_and_rho<<<cdiv(w->m, 256), 256, 0, w->stream>>>(w->m, w->l.p, w->u.p, st->rho, st->rho_is_vec, w->ctype.p,
+    k_type_and_rho<<<cdiv(w->m, 256), 256, 0, w->stream>>>(w->m, w->l.p, w->u.p, st->rho, st->rho_is_vec, w->rho_eq_factor, w->ctype.p,
                                                            w->rho_v.p, w->rho_inv.p, retype ? 1 : 0);
   k_jacobi<<<cdiv((long long)w->n * 8, 256), 256, 0, w->stream>>>(w->At.view(), w->pdiag.p, w->rho_v.p, st->sigma,
                                                                  st->cg_precond == B200QP_DIAGONAL_PRECONDITIONER,
@@ -257,6 +262,7 @@ KArgs make_args(b200qp_solver* sv) {
   a.sigma = st->sigma; a.alpha = st->alpha; a.rho = st->rho; a.eps_abs = st->eps_abs; a.eps_rel = st->eps_rel;
   a.eps_pinf = st->eps_prim_inf; a.eps_dinf = st->eps_dual_inf; a.c = w->c; a.adapt_tol = st->adaptive_rho_tolerance;
   a.cg_tol_frac = st->cg_tol_fraction;
+  a.rho_eq_factor = w->rho_eq_factor;
   a.unscale = (st->scaling && !st->scaled_termination) ? 1 : 0;
   a.nq_s = w->nq_s; a.nq_t = a.unscale ? w->nq_t : w->nq_s;
   a.time_limit_ns = st->time_limit * 1e9;
@@ -344,7 +350,7 @@ void b200qp_set_default_settings(b200qp_settings* s) {
   s->alpha = 1.6;
   s->cg_max_iter = 100;
   s->cg_tol_reduction = 10;
-  s->cg_tol_fraction = 0.15;
+  s->cg_tol_fraction = 0.05;
   s->cg_precond = B200QP_DIAGONAL_PRECONDITIONER;
   s->adaptive_rho = 1;
   s->adaptive_rho_interval = 50;
@@ -410,6 +416,7 @@ b200qp_int b200qp_setup(b200qp_solver** solverp, const b200qp_csc* P, const b200
   sv->settings->rho = std::min(std::max(settings->rho, RHO_MIN), RHO_MAX);
   try {
     w->n = n; w->m = m; w->device = settings->device;
+    if (const char* e = std::getenv("B200QP_RHO_EQ_FACTOR")) { const double f = std::atof(e); if (f >= 1.0 && f <= 1e6) w->rho_eq_factor = f; }
     CK(cudaSetDevice(w->device));
     int coop = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, w->device));
@@ -961,8 +968,104 @@ b200qp_int b200qp_spmv_csr_host(b200qp_int rows, b200qp_int cols, const b200qp_i
 
 }  // extern "C"
 
-// ---- polish: placeholder until polish.cuh lands (status_polish = 0: not performed) ------------------
-static int polish_impl(b200qp_solver* solver) {
-  solver->info->status_polish = 0;
+// ---- polish (reference: _osqp.py:1710-1828) ---------------------------------------------------------
+// The reference factorises the delta-regularised KKT system of the guessed active set and refines it.
+// Here the same equality-constrained QP (active rows pinned to their bound, inactive rows released) is
+// handed back to the persistent ADMM kernel: with z fixed at the bounds the iteration is the proximal
+// method of multipliers on that QP, whose inner systems P + sigma I + rho_eq Ared'Ared the PCG already
+// solves.  The acceptance test against the ADMM residuals (ref:1786-1793) is the reference's.
+static double reduce_absmax(Work* w, int len, const double* v, double* sum_out = nullptr) {
+  double h[2] = {0, 0};
+  if (len) {
+    k_absmax_sum<<<1, 1024, 0, w->stream>>>(len, v, nullptr, w->scal.p + 4);
+    CK(cudaMemcpyAsync(h, w->scal.p + 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+  }
+  if (sum_out) *sum_out = h[1];
+  return h[0];
+}
+
+static int polish_impl(b200qp_solver* sv) {
+  Work* w = W(sv);
+  b200qp_settings* st = sv->settings;
+  b200qp_info* info = sv->info;
+  const int n = w->n, m = w->m;
+  cudaStream_t s = w->stream;
+  info->status_polish = 0;
+  try {
+    if (!w->bk_x.p) {
+      for (DBuf<double>* b : {&w->pol_Minv, &w->bk_x}) b->alloc(n);
+      for (DBuf<double>* b : {&w->pol_l, &w->pol_u, &w->pol_rho, &w->pol_rhoinv, &w->bk_z, &w->bk_y, &w->bk_ax}) b->alloc(m);
+      w->pol_ctype.alloc(m); w->pol_count.alloc(1);
+    }
+    CK(cudaMemcpyAsync(w->bk_x.p, w->x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (m) {
+      CK(cudaMemcpyAsync(w->bk_z.p, w->z.p, m * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpyAsync(w->bk_y.p, w->y.p, m * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpyAsync(w->bk_ax.p, w->ax.p, m * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      w->pol_count.zero(s);
+      k_polish_prepare<<<cdiv(m, 256), 256, 0, s>>>(m, w->l.p, w->u.p, w->bk_z.p, w->ax.p, 1e3 * st->rho, w->y.p, w->z.p,
+                                                    w->pol_l.p, w->pol_u.p, w->pol_ctype.p, w->pol_rho.p,
+                                                    w->pol_rhoinv.p, w->pol_count.p);
+    }
+    k_jacobi<<<cdiv((long long)n * 8, 256), 256, 0, s>>>(w->At.view(), w->pdiag.p, w->pol_rho.p, st->sigma,
+                                                        st->cg_precond == B200QP_DIAGONAL_PRECONDITIONER, w->pol_Minv.p);
+    KArgs a = make_args(sv);
+    a.l = w->pol_l.p; a.u = w->pol_u.p; a.ctype = w->pol_ctype.p; a.rho_v = w->pol_rho.p; a.rho_inv = w->pol_rhoinv.p;
+    a.Minv = w->pol_Minv.p;
+    a.polish_mode = 1;
+    a.adaptive_rho = 0;
+    a.verbose = 0;
+    a.check_dualgap = 0;
+    a.eps_abs = a.eps_rel = std::max(1e-13, 1e-4 * std::min(st->eps_abs > 0 ? st->eps_abs : st->eps_rel,
+                                                              st->eps_rel > 0 ? st->eps_rel : st->eps_abs));
+    a.max_iter = 50 * std::max(1, st->polish_refine_iter);
+    a.check_term = 5;
+    a.cg_max_iter = std::max(4 * st->cg_max_iter, 200);
+    a.cg_tol_frac = std::min(st->cg_tol_fraction, 0.05);
+    a.time_limit_ns = 1e300;
+    const KOut admm = w->h_out;
+    float ms = 0.f;
+    run_admm(sv, a, &ms);
+    const KOut pol = w->h_out;
+    w->h_out = admm;
+    if (pol.aborted || pol.status == 0 || pol.status == B200QP_NON_CVX) throw (int)-1;
+
+    // residuals of the polished point on the ORIGINAL problem (ref:1779-1783)
+    const bool unscale = st->scaling && !st->scaled_termination;
+    double pri = 0.0;
+    if (m) {
+      k_polish_normalcone<<<cdiv(m, 256), 256, 0, s>>>(m, w->ax.p, w->l.p, w->u.p, unscale ? w->Einv.p : nullptr,
+                                                       w->y.p, w->z.p, w->tmp_m.p);
+      pri = reduce_absmax(w, m, w->tmp_m.p);
+      k_spmv_simple<<<cdiv((long long)n * 8, 256), 256, 0, s>>>(w->At.view(), w->y.p, w->tmp_n2.p);
+    } else {
+      CK(cudaMemsetAsync(w->tmp_n2.p, 0, n * sizeof(double), s));
+    }
+    k_spmv_simple<<<cdiv((long long)n * 8, 256), 256, 0, s>>>(w->P.view(), w->x.p, w->px.p);
+    k_polish_dual<<<cdiv(n, 256), 256, 0, s>>>(n, w->px.p, w->q.p, w->tmp_n2.p, unscale ? w->Dinv.p : nullptr, w->x.p,
+                                               w->tmp_n.p, w->kp.p);
+    const double dua = reduce_absmax(w, n, w->tmp_n.p) * (unscale ? 1.0 / w->c : 1.0);
+    double objsum = 0.0;
+    reduce_absmax(w, n, w->kp.p, &objsum);
+    const double obj = objsum / w->c;
+    const bool ok = (pri < info->prim_res && dua < info->dual_res) || (pri < info->prim_res && info->dual_res < 1e-10) ||
+                    (dua < info->dual_res && info->prim_res < 1e-10);
+    if (!ok) throw (int)-1;
+    info->obj_val = obj; info->prim_res = pri; info->dual_res = dua;
+    info->status_polish = 1;
+    w->stats.kernel_ms += ms;
+  } catch (int code) {
+    // unsuccessful: put the ADMM iterates back (ref:1813-1814)
+    info->status_polish = -1;
+    cudaMemcpyAsync(w->x.p, w->bk_x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    if (m) {
+      cudaMemcpyAsync(w->z.p, w->bk_z.p, m * sizeof(double), cudaMemcpyDeviceToDevice, s);
+      cudaMemcpyAsync(w->y.p, w->bk_y.p, m * sizeof(double), cudaMemcpyDeviceToDevice, s);
+      cudaMemcpyAsync(w->ax.p, w->bk_ax.p, m * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    }
+    cudaStreamSynchronize(s);
+    if (code > 0) return code;
+  }
   return 0;
 }

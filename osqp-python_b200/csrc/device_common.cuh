@@ -13,7 +13,7 @@ constexpr int NW = NT / 32;    // warps per CTA
 constexpr int KMAX = 16;       // max reduction slots per phase
 constexpr double QP_INFTY = 1e30;
 constexpr double INF_THRESH = 1e26;   // OSQP_INFTY * MIN_SCALING: bound counts as infinite
-constexpr double RHO_MIN = 1e-6, RHO_MAX = 1e6, RHO_EQ_FACTOR = 1e3, RHO_TOL = 1e-4;
+constexpr double RHO_MIN = 1e-6, RHO_MAX = 1e6, RHO_TOL = 1e-4;
 constexpr double MIN_SCALING = 1e-4, MAX_SCALING = 1e4;
 
 struct CsrMat {
