@@ -199,6 +199,23 @@ b200qp_int b200qp_update_settings(b200qp_solver *solver, const b200qp_settings *
 b200qp_int b200qp_update_rho(b200qp_solver *solver, b200qp_float rho_new);
 b200qp_int b200qp_get_stats(const b200qp_solver *solver, b200qp_stats *stats);
 
+/* ---- multi-GPU: ONE QP row-partitioned over `world` GPUs (BASELINE.json configs[3]) ----
+ * Not in the reference (its CUDA algebra is single-GPU: OSQPSettings.device is one int,
+ * src/bindings.cpp.in:409).  Every rank passes the full problem and settings->device = its GPU; rank g
+ * keeps a slab of constraint rows.  Connect the ranks once (cudaIpc handles between processes, or
+ * b200qp_dist_connect_local inside one process), then call b200qp_solve on every rank concurrently
+ * (or b200qp_dist_solve_group).  After a solve solution->x is complete on every rank; solution->y and
+ * prim_inf_cert are valid on the rank's own rows [mlo, mhi) only. */
+b200qp_int b200qp_dist_setup(b200qp_solver **solverp, b200qp_int rank, b200qp_int world,
+                             b200qp_int ranks_on_device, const b200qp_csc *P, const b200qp_float *q,
+                             const b200qp_csc *A, const b200qp_float *l, const b200qp_float *u, b200qp_int m,
+                             b200qp_int n, const b200qp_settings *settings);
+b200qp_int b200qp_dist_row_range(const b200qp_solver *solver, b200qp_int *mlo, b200qp_int *mhi);
+b200qp_int b200qp_dist_get_handle(b200qp_solver *solver, void *handle64);
+b200qp_int b200qp_dist_connect_ipc(b200qp_solver *solver, const void *handles_world_x_64);
+b200qp_int b200qp_dist_connect_local(b200qp_solver **group, b200qp_int world);
+b200qp_int b200qp_dist_solve_group(b200qp_solver **group, b200qp_int world);
+
 /* ---- hot operator, standalone (parity tests and the SpMV roofline line of bench.py) --------
  * y = M x for a CSR matrix (fp64 values, int32 indices).  *_host: host buffers in and out.
  * The device-handle form keeps the matrix and vectors resident and times `reps` launches with

@@ -26,6 +26,7 @@ struct KOut {                 // written by CTA 0 at kernel exit, read back by t
   long long cg_iters; long long barriers;
   double obj, dual_obj, gap, prim_res, dual_res, rho_estimate, rho, rel_kkt;
   int log_rows; int pad;
+  long long xepoch;           // multi-GPU kernel: cross-GPU barriers completed (carried to the next launch)
 };
 
 struct KArgs {

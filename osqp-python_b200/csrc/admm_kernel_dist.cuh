@@ -1,0 +1,606 @@
+// admm_kernel_dist.cuh -- the persistent ADMM kernel for ONE QP row-partitioned over several GPUs.
+//
+// Partition: rank g owns a contiguous slab of constraint rows (A_g, z, y, l, u, rho,
+// A x slab) and a slice of the variable space for the reduce step; the n-vectors (x, d, r, p, Kp,
+// Minv) are replicated.  Each rank runs this kernel as its own cooperative launch; ranks meet at
+// cross-GPU barriers built on flags in peer-mapped memory (NVLink / NVSwitch), no host in the loop.
+//
+// The one exchange step of the path -- "sum over ranks of A_g' w_g" -- is fused into the kernels
+// that produce and consume it (no NCCL call, no extra launch):
+//     a) every rank writes its partial n-vector A_g' w_g into its own memory             (SpMV)
+//     b) cross-GPU barrier
+//     c) rank g reads slice g of every rank's partial over NVLink in rank order, adds its P-rows
+//        and sigma, forms Kp (or r, p), the dot-product partial, and pushes the finished slice
+//        into every rank's copy                                                          (reduce-scatter
+//        + compute + all-gather in one phase)
+//     d) cross-GPU barrier carrying the scalar partials (dots / norms) as payload
+// Summation order over ranks is fixed and every rank receives the same bits, so all ranks take
+// identical control decisions.  Everything else (C1, C3, C4, Z) is rank-local.
+#pragma once
+#include "admm_kernel.cuh"
+
+namespace b200qp {
+
+constexpr int MAXW = 8;
+
+struct XArgs {
+  int rank, world;
+  int slice[MAXW + 1];              // variable-space slice boundaries
+  // peer-mapped tables: entry h points into rank h's shared region
+  double* part_w[MAXW];             // partial n-vector #1
+  double* part_y[MAXW];             // partial n-vector #2 (A'y on check iterations, Jacobi sums)
+  double* r[MAXW];
+  double* p[MAXW];
+  double* kp[MAXW];
+  double* Minv[MAXW];
+  unsigned long long* flags[MAXW];  // rank h's arrival counters, one per source rank
+  double* payload[MAXW];            // rank h's payload area [2][MAXW][KMAX]
+  int* abort_flag[MAXW];
+  // local scratch
+  double* sum_w; double* sum_y;     // reduced partials for my slice (full-length buffers, slice used)
+  double* xtot;                     // [2][KMAX] totals published by CTA 0 to the other CTAs
+  unsigned long long* release;      // local release counter of the cross-GPU barrier
+  const int *part_nfull, *part_slice, *part_uni;   // CTA partitions: A_g' rows, my slice by P, uniform n
+  unsigned long long xepoch0;       // cross-GPU barriers completed by earlier launches (flags are never reset)
+};
+
+__device__ __forceinline__ double ld_peer(const double* p) {   // bypass L1: peer data is not L2-cached locally
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_sys_f64(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// Local grid barrier + cross-GPU barrier, optionally all-reducing K scalars.
+//   every CTA : block partials already in `bank` (if K) ; arrive
+//   CTA 0     : wait for local arrivals, fold the local partials, publish them to every rank with an
+//               arrival flag, wait for every rank, fold all ranks' payloads in rank order, release
+//   every CTA : totals in s_tot[0..K)
+struct DistSync {
+  GridSync* g;
+  const XArgs* x;
+  unsigned long long xepoch;     // cross-GPU barriers passed
+
+  template <int K>
+  __device__ __forceinline__ bool barrier_x(const double* bank, unsigned maxmask, double* s_tot) {
+    const int G = g->G, world = x->world, tid = threadIdx.x;
+    __threadfence_system();
+    __syncthreads();
+    g->epoch++;
+    xepoch++;
+    const int par = (int)(xepoch & 1ULL);
+    bool ok = true;
+    if (blockIdx.x == 0) {
+      // 1. wait for every local CTA
+      if (tid == 0 && G == 1) *g->s_ok = 1;
+      if (tid == 0 && G > 1) {
+        __threadfence();
+        atomicAdd(&g->ctrl->bar, 1ULL);
+        const unsigned long long target = g->epoch * (unsigned long long)G;
+        unsigned spins = 0; unsigned long long t0 = 0;
+        while (ld_acquire_u64(&g->ctrl->bar) < target) {
+          if ((++spins & 0xfffu) == 0) {
+            if (*(volatile int*)&g->ctrl->abort) { ok = false; break; }
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now; else if (now - t0 > 10000000000ULL) { atomicExch(&g->ctrl->abort, 1); ok = false; break; }
+          }
+        }
+        __threadfence();
+        *g->s_ok = ok ? 1 : 0;
+      }
+      __syncthreads();
+      ok = *g->s_ok != 0;
+      // 2. local totals
+      if (K > 0 && ok) grid_reduce_load<(K > 0 ? K : 1)>(bank, G, maxmask, s_tot);
+      // 3. publish payload + arrival flag to every rank (thread h talks to rank h)
+      if (ok && tid < world) {
+        double* dst = x->payload[tid] + ((size_t)par * MAXW + x->rank) * KMAX;
+        for (int k = 0; k < K; ++k) st_sys_f64(dst + k, s_tot[k]);
+        __threadfence_system();
+        st_release_sys_u64(x->flags[tid] + x->rank, xepoch);
+      }
+      // 4. wait for every rank's arrival (their flags live in my memory)
+      if (ok && tid < world) {
+        unsigned spins = 0; unsigned long long t0 = 0;
+        const unsigned long long* f = x->flags[x->rank] + tid;
+        while (ld_acquire_sys_u64(f) < xepoch) {
+          if ((++spins & 0x3ffu) == 0) {
+            if (*(volatile int*)&g->ctrl->abort) { ok = false; break; }
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now; else if (now - t0 > 10000000000ULL) { atomicExch(&g->ctrl->abort, 1); ok = false; break; }
+          }
+        }
+        if (!ok) *g->s_ok = 0;
+      }
+      __syncthreads();
+      ok = *g->s_ok != 0;
+      // 5. fold the payloads of all ranks in rank order, publish to the local CTAs, release
+      if (ok && tid < K) {
+        const bool mx = (maxmask >> tid) & 1u;
+        const double* src = x->payload[x->rank] + (size_t)par * MAXW * KMAX;
+        double acc = __ldcv(src + tid);
+        for (int h = 1; h < world; ++h) acc = combine(acc, __ldcv(src + (size_t)h * KMAX + tid), mx);
+        x->xtot[par * KMAX + tid] = acc;
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        if (!ok) atomicExch(&g->ctrl->abort, 1);
+        __threadfence();
+        atomicExch(x->release, g->epoch);     // monotone: release value = local epoch
+      }
+    } else {
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(&g->ctrl->bar, 1ULL);
+        unsigned spins = 0; unsigned long long t0 = 0;
+        int good = 1;
+        while (ld_acquire_u64(x->release) < g->epoch) {
+          if ((++spins & 0xfffu) == 0) {
+            if (*(volatile int*)&g->ctrl->abort) { good = 0; break; }
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now; else if (now - t0 > 12000000000ULL) { atomicExch(&g->ctrl->abort, 1); good = 0; break; }
+          }
+        }
+        __threadfence();
+        if (*(volatile int*)&g->ctrl->abort) good = 0;
+        *g->s_ok = good;
+      }
+      __syncthreads();
+      ok = *g->s_ok != 0;
+    }
+    if (ok && K > 0) {
+      if (tid < K) s_tot[tid] = __ldcg(x->xtot + par * KMAX + tid);
+      __syncthreads();
+    }
+    if (!ok) {   // tell the other ranks so that nobody spins until the watchdog
+      if (blockIdx.x == 0 && tid < world) *(volatile int*)x->abort_flag[tid] = 1;
+    }
+    return ok;
+  }
+};
+
+#define B200QP_XBAR_OR_DIE(K, bank, mask) do { if (!xs.template barrier_x<K>(bank, mask, s_tot)) { if (blockIdx.x == 0 && threadIdx.x == 0) a.out->aborted = 1; return; } } while (0)
+
+template <int LGN, int LGM>
+__global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant__ KArgs a, const __grid_constant__ XArgs x) {
+  __shared__ double s_red[KMAX * NW];
+  __shared__ double s_tot[KMAX];
+  __shared__ int s_ok;
+
+  const int G = a.G, cta = blockIdx.x, tid = threadIdx.x;
+  const int rank = x.rank, world = x.world;
+  const int f0 = x.part_nfull[cta], f1 = x.part_nfull[cta + 1];     // rows of A_g' handled by this CTA
+  const int s0 = x.part_slice[cta], s1 = x.part_slice[cta + 1];     // my share of this rank's slice
+  const int u0 = x.part_uni[cta], u1 = x.part_uni[cta + 1];         // uniform share of [0, n) (replicated work)
+  const int m0 = a.part_m[cta], m1 = a.part_m[cta + 1];
+  GridSync sync{a.ctrl, G, 0ULL, &s_ok};
+  DistSync xs{&sync, &x, x.xepoch0};
+  const double NEG_INF = __longlong_as_double(0xfff0000000000000LL);
+
+  constexpr int NGN = NT / LGN, NGM = NT / LGM;
+  const int lane_n = tid & (LGN - 1), grp_n = tid / LGN;
+  const int lane_m = tid & (LGM - 1), grp_m = tid / LGM;
+
+  const double alpha = a.alpha, sigma = a.sigma;
+  const double cinv = 1.0 / a.c;
+  const double c_eff = a.unscale ? a.c : 1.0, cinv_eff = a.unscale ? cinv : 1.0;
+  const double* Dinv_t = a.unscale ? a.Dinv : nullptr;
+  const double* D_t = a.unscale ? a.D : nullptr;
+  const double* Einv_t = a.unscale ? a.Einv : nullptr;
+  const double* E_t = a.unscale ? a.E : nullptr;
+
+  double* my_part_w = x.part_w[rank];
+  double* my_part_y = x.part_y[rank];
+
+  double rho = a.rho;
+  int rho_updates = 0, status = 0, k = 0;
+  long long cg_total = 0;
+  const unsigned long long t_start = global_timer_ns();
+
+  double obj = 0, dobj = 0, gap = 0, prim_res = 0, dual_res = 0, nprim = 0, ndual = 0;
+  double s_prim = 0, s_nprim = 0, s_dual = 0, s_ndual = 0;
+  double ndy = 0, lhs = 0, vu = NEG_INF, vl = NEG_INF, sup = 0;
+  double t_prim = 0, t_ax = 0, t_z = 0;
+  double ndx = 0, qdx = 0;
+  double rz = 0, r0max = 0;
+  bool time_up = false;
+
+  auto bank = [&]() -> double* { return a.red + (size_t)(sync.epoch & 1ULL) * KMAX * G; };
+
+  // coalesced reduce-scatter pre-pass for this CTA's rows of the slice: sum over ranks, rank order
+  auto gather_partials = [&](bool second) {
+    for (int i = s0 + tid; i < s1; i += NT) {
+      double acc = ld_peer(x.part_w[0] + i);
+      for (int h = 1; h < world; ++h) acc += ld_peer(x.part_w[h] + i);
+      x.sum_w[i] = acc;
+      if (second) {
+        double acy = ld_peer(x.part_y[0] + i);
+        for (int h = 1; h < world; ++h) acy += ld_peer(x.part_y[h] + i);
+        x.sum_y[i] = acy;
+      }
+    }
+    __syncthreads();
+  };
+  // push this CTA's finished rows of a replicated vector to every other rank (all-gather by stores)
+  auto push_rows = [&](double* const* table, const double* local) {
+    for (int h = 0; h < world; ++h) {
+      if (h == rank) continue;
+      double* dst = table[h];
+      for (int i = s0 + tid; i < s1; i += NT) st_sys_f64(dst + i, __ldcg(local + i));
+    }
+  };
+
+  // ------------------------------------------------------------------ init: ax = A_g x, w2
+  for (int base = m0; base < m1; base += NGM) {
+    const int row = base + grp_m;
+    const bool valid = row < m1;
+    const double acc = group_sum<LGM>(row_dot<LGM>(a.A, a.x, row, valid, lane_m));
+    if (valid && lane_m == 0) {
+      a.ax[row] = acc;
+      a.w2[row] = a.rho_v[row] * (a.z[row] - acc) - a.y[row];
+    }
+  }
+  B200QP_BARRIER_OR_DIE();
+
+  // ---- R phase, distributed: partial A_g' w2 (and A_g' y) -> reduce over ranks -> r, p everywhere
+  auto phase_R = [&](bool full, bool lite) -> bool {
+    // R1: partials over all n rows of A_g'
+    for (int base = f0; base < f1; base += NGN) {
+      const int row = base + grp_n;
+      const bool valid = row < f1;
+      double atw = 0, sec = 0;
+      if (full) row_dot2<LGN>(a.At, a.w2, a.y, row, valid, lane_n, atw, sec);
+      else {
+        atw = row_dot<LGN>(a.At, a.w2, row, valid, lane_n);
+        if (lite && a.cg_precond) sec = row_dot_sq<LGN>(a.At, a.rho_v, row, valid, lane_n);
+      }
+      atw = group_sum<LGN>(atw);
+      sec = group_sum<LGN>(sec);
+      if (valid && lane_n == 0) {
+        my_part_w[row] = atw;
+        if (full || lite) my_part_y[row] = sec;
+      }
+    }
+    if (!xs.template barrier_x<0>(nullptr, 0u, s_tot)) return false;
+    // R2: my slice
+    gather_partials(full || lite);
+    double v[R_K];
+#pragma unroll
+    for (int i = 0; i < R_K; ++i) v[i] = 0.0;
+    for (int base = s0; base < s1; base += NGN) {
+      const int row = base + grp_n;
+      const bool valid = row < s1;
+      double px = 0;
+      if (!lite) px = group_sum<LGN>(row_dot<LGN>(a.P, a.x, row, valid, lane_n));
+      if (valid && lane_n == 0) {
+        const double qj = a.q[row];
+        if (lite) {
+          px = a.px[row];
+          if (a.cg_precond) a.Minv[row] = 1.0 / (a.pdiag[row] + sigma + __ldcg(x.sum_y + row));
+        }
+        const double atw = __ldcg(x.sum_w + row);
+        const double rj = -(px + qj) + atw;
+        const double pj = __ldcg(a.Minv + row) * rj;
+        a.r[row] = rj;
+        a.p[row] = pj;
+        v[R_RZ] += rj * pj;
+        v[R_R0] = nanmax(v[R_R0], fabs(rj));
+        if (full) {
+          a.px[row] = px;
+          const double aty = __ldcg(x.sum_y + row);
+          const double xj = __ldcg(a.x + row), dj = alpha * __ldcg(a.d + row);
+          const double dres = px + qj + aty;
+          const double di = Dinv_t ? Dinv_t[row] : 1.0;
+          v[R_SDUAL] = nanmax(v[R_SDUAL], fabs(dres));
+          v[R_SATY] = nanmax(v[R_SATY], fabs(aty));
+          v[R_SPX] = nanmax(v[R_SPX], fabs(px));
+          v[R_TDUAL] = nanmax(v[R_TDUAL], fabs(di * dres));
+          v[R_TATY] = nanmax(v[R_TATY], fabs(di * aty));
+          v[R_TPX] = nanmax(v[R_TPX], fabs(di * px));
+          v[R_XPX] += xj * px;
+          v[R_QX] += qj * xj;
+          v[R_NDX] = nanmax(v[R_NDX], fabs((D_t ? D_t[row] : 1.0) * dj));
+          v[R_QDX] += qj * dj;
+        }
+      }
+    }
+    if (full && tid == 0)
+      v[R_TL] = ((double)(global_timer_ns() - t_start) > a.time_limit_ns) ? 1.0 : 0.0;
+    __syncthreads();
+    push_rows(x.r, a.r);
+    push_rows(x.p, a.p);
+    if (lite && a.cg_precond) push_rows(x.Minv, a.Minv);
+    double* bk = bank();
+    block_reduce_store<R_K>(v, R_MAXMASK, bk, G, s_red);
+    if (!xs.template barrier_x<R_K>(bk, R_MAXMASK, s_tot)) return false;
+    rz = s_tot[R_RZ];
+    r0max = s_tot[R_R0];
+    if (full) {
+      s_dual = s_tot[R_SDUAL];
+      s_ndual = fmax(fmax(s_tot[R_SATY], s_tot[R_SPX]), a.nq_s);
+      dual_res = cinv_eff * s_tot[R_TDUAL];
+      ndual = cinv_eff * fmax(fmax(s_tot[R_TATY], s_tot[R_TPX]), a.nq_t);
+      obj = (0.5 * s_tot[R_XPX] + s_tot[R_QX]) * cinv;
+      dobj = (-0.5 * s_tot[R_XPX] - sup) * cinv;
+      gap = obj - dobj;
+      ndx = s_tot[R_NDX];
+      qdx = s_tot[R_QDX];
+      time_up = s_tot[R_TL] > 0.5;
+      prim_res = t_prim;
+      nprim = fmax(t_ax, t_z);
+    }
+    return true;
+  };
+
+  // |Dinv .* scale .* (A' vec)|inf (vec is an m-slab vector) or |Dinv .* scale .* (P vec)|inf
+  auto cert_norm_At = [&](const double* vec, bool& ok) -> double {
+    for (int base = f0; base < f1; base += NGN) {
+      const int row = base + grp_n;
+      const bool valid = row < f1;
+      const double acc = group_sum<LGN>(row_dot<LGN>(a.At, vec, row, valid, lane_n));
+      if (valid && lane_n == 0) my_part_w[row] = acc;
+    }
+    ok = xs.template barrier_x<0>(nullptr, 0u, s_tot);
+    if (!ok) return 0.0;
+    gather_partials(false);
+    double v[1] = {0.0};
+    for (int i = s0 + tid; i < s1; i += NT) v[0] = nanmax(v[0], fabs((Dinv_t ? Dinv_t[i] : 1.0) * __ldcg(x.sum_w + i)));
+    double* bk = bank();
+    block_reduce_store<1>(v, 1u, bk, G, s_red);
+    ok = xs.template barrier_x<1>(bk, 1u, s_tot);
+    return ok ? s_tot[0] : 0.0;
+  };
+  auto cert_norm_P = [&](const double* vec, double scale, bool& ok) -> double {
+    double v[1] = {0.0};
+    for (int base = s0; base < s1; base += NGN) {
+      const int row = base + grp_n;
+      const bool valid = row < s1;
+      const double acc = group_sum<LGN>(row_dot<LGN>(a.P, vec, row, valid, lane_n));
+      if (valid && lane_n == 0) v[0] = nanmax(v[0], fabs((Dinv_t ? Dinv_t[row] : 1.0) * scale * acc));
+    }
+    double* bk = bank();
+    block_reduce_store<1>(v, 1u, bk, G, s_red);
+    ok = xs.template barrier_x<1>(bk, 1u, s_tot);
+    return ok ? s_tot[0] : 0.0;
+  };
+
+  auto evaluate = [&](double f, bool& ok) -> int {
+    ok = true;
+    if (!(prim_res <= QP_INFTY) || !(dual_res <= QP_INFTY)) return 9;
+    const double ea = f * a.eps_abs, er = f * a.eps_rel;
+    const bool prim_ok = (a.m == 0 && world == 1) ? true : (prim_res < ea + er * nprim);
+    const bool dual_ok = dual_res < ea + er * ndual;
+    const bool gap_ok = !a.check_dualgap || (fabs(gap) < ea + er * fmax(fabs(obj), fabs(dobj)));
+    if (prim_ok && dual_ok && gap_ok) return f > 1.0 ? 2 : 1;
+    if (a.polish_mode) return 0;
+    if (!prim_ok) {
+      const double eps = f * a.eps_pinf;
+      if (ndy > eps && lhs < -eps * ndy) {
+        const double nat = cert_norm_At(a.w, ok);
+        if (!ok) return 0;
+        if (nat < eps * ndy) return f > 1.0 ? 4 : 3;
+      }
+    }
+    if (!dual_ok) {
+      const double eps = f * a.eps_dinf;
+      if (ndx > eps && qdx < -c_eff * eps * ndx && vu <= eps * ndx && vl <= eps * ndx) {
+        const double npd = cert_norm_P(a.d, alpha, ok);
+        if (!ok) return 0;
+        if (npd < c_eff * eps * ndx) return f > 1.0 ? 6 : 5;
+      }
+    }
+    return 0;
+  };
+
+#define B200QP_DIE() do { if (cta == 0 && tid == 0) a.out->aborted = 1; return; } while (0)
+
+  // ================================================================== main loop
+  for (;;) {
+    const bool last = (k >= a.max_iter);
+    const bool chk = k > 0 && ((a.check_term > 0 && (k % a.check_term) == 0) || last);
+    const bool adp = k > 0 && !last && a.adaptive_rho && a.adapt_interval > 0 && (k % a.adapt_interval) == 0;
+    const bool full = chk || adp;
+
+    if (!phase_R(full, false)) B200QP_DIE();
+    if (full && a.verbose && cta == 0 && tid == 0 && chk && rank == 0) {
+      const int row = (k / (a.check_term > 0 ? a.check_term : 1)) - 1;
+      if (row >= 0 && row < a.log_cap) {
+        a.log[row] = LogRow{k, 0, obj, prim_res, dual_res, rho, (double)(global_timer_ns() - t_start) * 1e-6};
+        a.out->log_rows = row + 1;
+      }
+    }
+    if (chk) {
+      bool ok;
+      status = evaluate(1.0, ok);
+      if (!ok) B200QP_DIE();
+      if (status) break;
+      if (last) {
+        status = evaluate(10.0, ok);
+        if (!ok) B200QP_DIE();
+        if (!status) status = 7;
+        break;
+      }
+      if (time_up) { status = 8; break; }
+    }
+    if (adp) {
+      const double pr = s_prim / (s_nprim + 1e-10);
+      const double du = s_dual / (s_ndual + 1e-10);
+      double rho_new = rho * sqrt(pr / (du + 1e-10));
+      rho_new = fmin(fmax(rho_new, RHO_MIN), RHO_MAX);
+      if (rho_new > a.adapt_tol * rho || rho_new < rho / a.adapt_tol) {
+        rho = rho_new;
+        rho_updates++;
+        for (int i = m0 + tid; i < m1; i += NT) {
+          const double rv = rho_of_type(a.ctype[i], rho, a.rho_is_vec, a.rho_eq_factor);
+          a.rho_v[i] = rv;
+          a.rho_inv[i] = 1.0 / rv;
+          a.w2[i] = rv * (a.z[i] - a.ax[i]) - a.y[i];
+        }
+        B200QP_BARRIER_OR_DIE();
+        if (!phase_R(false, true)) B200QP_DIE();
+      }
+    }
+
+    // ---------------------------------------------------------------- PCG on K d = r
+    bool have_d = false;
+    if (r0max > 1e-150) {
+      const double tol = a.cg_tol_frac * r0max;
+      for (int j = 0; j < a.cg_max_iter; ++j) {
+        // C1 (local rows): w = rho .* (A_g p)
+        for (int base = m0; base < m1; base += NGM) {
+          const int row = base + grp_m;
+          const bool valid = row < m1;
+          const double acc = group_sum<LGM>(row_dot<LGM>(a.A, a.p, row, valid, lane_m));
+          if (valid && lane_m == 0) a.w[row] = a.rho_v[row] * acc;
+        }
+        B200QP_BARRIER_OR_DIE();
+        // C2a: partial A_g' w over all n rows
+        for (int base = f0; base < f1; base += NGN) {
+          const int row = base + grp_n;
+          const bool valid = row < f1;
+          const double acc = group_sum<LGN>(row_dot<LGN>(a.At, a.w, row, valid, lane_n));
+          if (valid && lane_n == 0) my_part_w[row] = acc;
+        }
+        B200QP_XBAR_OR_DIE(0, nullptr, 0u);
+        // C2b: my slice: Kp = sum_h partial_h + P p + sigma p ; <p, Kp> partial ; push Kp
+        gather_partials(false);
+        double v1[1] = {0.0};
+        for (int base = s0; base < s1; base += NGN) {
+          const int row = base + grp_n;
+          const bool valid = row < s1;
+          const double acc = group_sum<LGN>(row_dot<LGN>(a.P, a.p, row, valid, lane_n));
+          if (valid && lane_n == 0) {
+            const double pj = __ldcg(a.p + row);
+            const double kpj = acc + sigma * pj + __ldcg(x.sum_w + row);
+            a.kp[row] = kpj;
+            v1[0] += pj * kpj;
+          }
+        }
+        __syncthreads();
+        push_rows(x.kp, a.kp);
+        double* bk = bank();
+        block_reduce_store<1>(v1, 0u, bk, G, s_red);
+        B200QP_XBAR_OR_DIE(1, bk, 0u);
+        const double pkp = s_tot[0];
+        if (!(pkp > 0.0)) { status = 9; break; }
+        const double aj = rz / pkp;
+        cg_total++;
+        // C3 (replicated, uniform partition): d += a p ; r -= a Kp ; <r, Minv r> ; |r|inf
+        double v2[2] = {0.0, 0.0};
+        for (int i = u0 + tid; i < u1; i += NT) {
+          const double pi = __ldcg(a.p + i);
+          a.d[i] = (j == 0) ? aj * pi : fma(aj, pi, __ldcg(a.d + i));
+          const double ri = fma(-aj, __ldcg(a.kp + i), __ldcg(a.r + i));
+          a.r[i] = ri;
+          v2[0] += ri * __ldcg(a.Minv + i) * ri;
+          v2[1] = nanmax(v2[1], fabs(ri));
+        }
+        have_d = true;
+        bk = bank();
+        block_reduce_store<2>(v2, 2u, bk, G, s_red);
+        B200QP_BARRIER_OR_DIE();
+        grid_reduce_load<2>(bk, G, 2u, s_tot);
+        const double rz_new = s_tot[0], rmax = s_tot[1];
+        if (!(rmax > tol) || j + 1 == a.cg_max_iter) break;
+        const double bj = rz_new / rz;
+        rz = rz_new;
+        for (int i = u0 + tid; i < u1; i += NT) a.p[i] = fma(bj, __ldcg(a.p + i), __ldcg(a.Minv + i) * __ldcg(a.r + i));
+        B200QP_BARRIER_OR_DIE();
+      }
+      if (status) break;
+    }
+    if (!have_d) {
+      for (int i = u0 + tid; i < u1; i += NT) a.d[i] = 0.0;
+      B200QP_BARRIER_OR_DIE();
+    }
+
+    // ---------------------------------------------------------------- Z phase (local rows)
+    const int kn = k + 1;
+    const bool last_n = (kn >= a.max_iter);
+    const bool full_n = ((a.check_term > 0 && (kn % a.check_term) == 0) || last_n) ||
+                        (!last_n && a.adaptive_rho && a.adapt_interval > 0 && (kn % a.adapt_interval) == 0);
+    {
+      double v[Z_K];
+#pragma unroll
+      for (int i = 0; i < Z_K; ++i) v[i] = 0.0;
+      v[Z_VU] = NEG_INF; v[Z_VL] = NEG_INF;
+      for (int base = m0; base < m1; base += NGM) {
+        const int row = base + grp_m;
+        const bool valid = row < m1;
+        const double ad = group_sum<LGM>(row_dot<LGM>(a.A, a.d, row, valid, lane_m));
+        if (valid && lane_m == 0) {
+          const double ax_old = a.ax[row], z_old = a.z[row], y_old = a.y[row];
+          const double rv = a.rho_v[row], ri = a.rho_inv[row], li = a.l[row], ui = a.u[row];
+          const double zt = ax_old + ad;
+          const double zr = alpha * zt + (1.0 - alpha) * z_old;
+          const double zn = fmin(fmax(zr + ri * y_old, li), ui);
+          const double dy = rv * (zr - zn);
+          const double yn = y_old + dy;
+          const double axn = fma(alpha, ad, ax_old);
+          a.z[row] = zn; a.y[row] = yn; a.ax[row] = axn;
+          a.w2[row] = rv * (zn - axn) - yn;
+          if (full_n) {
+            const double ei = Einv_t ? Einv_t[row] : 1.0;
+            const double pr = axn - zn;
+            v[Z_SPRIM] = nanmax(v[Z_SPRIM], fabs(pr));
+            v[Z_SAX] = nanmax(v[Z_SAX], fabs(axn));
+            v[Z_SZ] = nanmax(v[Z_SZ], fabs(zn));
+            v[Z_TPRIM] = nanmax(v[Z_TPRIM], fabs(ei * pr));
+            v[Z_TAX] = nanmax(v[Z_TAX], fabs(ei * axn));
+            v[Z_TZ] = nanmax(v[Z_TZ], fabs(ei * zn));
+            const bool lfin = li > -INF_THRESH, ufin = ui < INF_THRESH;
+            double dyp = dy;
+            if (!ufin && !lfin) dyp = 0.0;
+            else if (!ufin) dyp = fmin(dy, 0.0);
+            else if (!lfin) dyp = fmax(dy, 0.0);
+            a.w[row] = dyp;
+            v[Z_NDY] = nanmax(v[Z_NDY], fabs((E_t ? E_t[row] : 1.0) * dyp));
+            v[Z_LHS] += (ufin ? ui * fmax(dyp, 0.0) : 0.0) + (lfin ? li * fmin(dyp, 0.0) : 0.0);
+            const double adx = ei * alpha * ad;
+            if (ufin) v[Z_VU] = nanmax(v[Z_VU], adx);
+            if (lfin) v[Z_VL] = nanmax(v[Z_VL], -adx);
+            v[Z_SUP] += (ufin ? ui * fmax(yn, 0.0) : 0.0) + (lfin ? li * fmin(yn, 0.0) : 0.0);
+          }
+        }
+      }
+      for (int i = u0 + tid; i < u1; i += NT) a.x[i] = fma(alpha, __ldcg(a.d + i), __ldcg(a.x + i));
+      if (full_n) {
+        double* bk = bank();
+        block_reduce_store<Z_K>(v, Z_MAXMASK, bk, G, s_red);
+        B200QP_XBAR_OR_DIE(Z_K, bk, Z_MAXMASK);
+        s_prim = s_tot[Z_SPRIM];
+        s_nprim = fmax(s_tot[Z_SAX], s_tot[Z_SZ]);
+        t_prim = s_tot[Z_TPRIM]; t_ax = s_tot[Z_TAX]; t_z = s_tot[Z_TZ];
+        ndy = s_tot[Z_NDY]; lhs = s_tot[Z_LHS]; vu = s_tot[Z_VU]; vl = s_tot[Z_VL]; sup = s_tot[Z_SUP];
+      } else {
+        B200QP_BARRIER_OR_DIE();
+      }
+    }
+    k = kn;
+  }
+
+  if (cta == 0 && tid == 0) {
+    KOut* o = a.out;
+    o->status = status; o->iter = k; o->rho_updates = rho_updates;
+    o->cg_iters = cg_total; o->barriers = (long long)sync.epoch;
+    o->xepoch = (long long)xs.xepoch;
+    o->obj = obj; o->dual_obj = dobj; o->gap = gap; o->prim_res = prim_res; o->dual_res = dual_res;
+    o->rho = rho;
+    const double pr = s_prim / (s_nprim + 1e-10), du = s_dual / (s_ndual + 1e-10);
+    o->rho_estimate = fmin(fmax(rho * sqrt(pr / (du + 1e-10)), RHO_MIN), RHO_MAX);
+    o->rel_kkt = fmax(prim_res / (nprim + 1e-10), dual_res / (ndual + 1e-10));
+  }
+}
+
+}  // namespace b200qp

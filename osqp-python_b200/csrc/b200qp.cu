@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "admm_kernel.cuh"
+#include "admm_kernel_dist.cuh"
 #include "aux_kernels.cuh"
 #include "spmv_kernels.cuh"
 
@@ -44,6 +45,8 @@ template <class T>
 struct DBuf {                     // device array
   T* p = nullptr;
   size_t n = 0;
+  bool owned = true;
+  void borrow(T* ptr, size_t cnt) { free(); p = ptr; n = cnt; owned = false; }   // view into another allocation
   void alloc(size_t cnt) {
     free();
     n = cnt;
@@ -54,9 +57,10 @@ struct DBuf {                     // device array
   }
   void zero(cudaStream_t s) { CK(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), s)); }
   void free() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr;
     n = 0;
+    owned = true;
   }
 };
 
@@ -135,9 +139,28 @@ struct Work {
   double c = 1.0;
   double rho_eq_factor = 10.0;   // engine default; reference uses 1e3; env B200QP_RHO_EQ_FACTOR
   double nq_s = 0, nq_t = 0;
-  int G = 1, lgn = 8, lgm = 8, max_coop = 1;
+  int G = 1, lgn = 8, lgm = 8, max_coop = 1, max_coop_dist = 1;
   bool first_run = true, clear_update_time = false;
   b200qp_stats stats{};
+  // ---- multi-GPU (row-partitioned single QP); world == 1 means plain single-GPU solver
+  struct Dist {
+    int rank = 0, world = 1, mlo = 0, mhi = 0;
+    int slice[MAXW + 1] = {0};
+    char* region = nullptr;            // my shared region (one allocation, peer-mapped)
+    size_t region_bytes = 0;
+    char* peer[MAXW] = {nullptr};      // base of every rank's region in my address space
+    bool opened[MAXW] = {false};       // cudaIpcOpenMemHandle'd (must be closed)
+    bool connected = false;
+    DevCsr Atg;                        // A_g' : n x m_g, compact
+    DBuf<double> sum_w, sum_y, xtot;
+    DBuf<unsigned long long> release;
+    DBuf<int> part_m, part_nfull, part_slice, part_uni;
+    int G = 1, lgn = 8, lgm = 8;
+    unsigned long long xepoch = 0;
+    bool broken = false;
+  } dist;
+  bool in_flight = false;
+  double t_solve_begin = 0;
   double *h_x = nullptr, *h_y = nullptr, *h_pc = nullptr, *h_dc = nullptr;  // pinned
   KOut h_out{};
 
@@ -151,6 +174,11 @@ struct Work {
       b->free();
     pol_ctype.free(); pol_count.free();
     ctype.free(); stage_i.free(); part_n.free(); part_m.free(); ctrl.free(); out.free(); log.free();
+    for (int h = 0; h < MAXW; ++h)
+      if (dist.opened[h] && dist.peer[h]) cudaIpcCloseMemHandle(dist.peer[h]);
+    if (dist.region) cudaFree(dist.region);
+    dist.Atg.free(); dist.sum_w.free(); dist.sum_y.free(); dist.xtot.free(); dist.release.free();
+    dist.part_m.free(); dist.part_nfull.free(); dist.part_slice.free(); dist.part_uni.free();
     if (h_x) cudaFreeHost(h_x);
     if (h_y) cudaFreeHost(h_y);
     if (h_pc) cudaFreeHost(h_pc);
@@ -158,6 +186,21 @@ struct Work {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+// shared-region layout of a multi-GPU rank (same offsets on every rank)
+struct RegionLayout {
+  size_t ctrl, flags, payload, part_w, part_y, r, p, kp, Minv, total;
+  explicit RegionLayout(size_t n) {
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o = 0;
+    ctrl = o; o = al(o + sizeof(Ctrl));
+    flags = o; o = al(o + MAXW * sizeof(unsigned long long));
+    payload = o; o = al(o + 2 * MAXW * KMAX * sizeof(double));
+    const size_t vec = al(n * sizeof(double));
+    part_w = o; o += vec; part_y = o; o += vec; r = o; o += vec; p = o; o += vec; kp = o; o += vec; Minv = o; o += vec;
+    total = o;
   }
 };
 
@@ -271,22 +314,90 @@ KArgs make_args(b200qp_solver* sv) {
   a.cg_max_iter = st->cg_max_iter; a.cg_precond = st->cg_precond == B200QP_DIAGONAL_PRECONDITIONER;
   a.rho_is_vec = st->rho_is_vec; a.check_dualgap = st->check_dualgap; a.verbose = st->verbose;
   a.polish_mode = 0;
+  if (w->dist.connected) {
+    // row slab views: A_g = rows [mlo, mhi) of CSR(A) (pointer offset), compact A_g', slab of every m-vector;
+    // r, p, Kp, Minv live in the shared region so that the other ranks can push their slices into them
+    Work::Dist& d = w->dist;
+    const int mlo = d.mlo, mg = d.mhi - d.mlo;
+    RegionLayout L(w->n);
+    a.m = mg; a.G = d.G;
+    a.A = CsrMat{mg, w->n, w->A.nnz, w->A.ptr.p + mlo, w->A.idx.p, w->A.val.p};
+    a.At = d.Atg.view();
+    a.l += mlo; a.u += mlo; a.E += mlo; a.Einv += mlo; a.ctype += mlo;
+    a.z += mlo; a.y += mlo; a.ax += mlo; a.w2 += mlo; a.w += mlo; a.rho_v += mlo; a.rho_inv += mlo;
+    a.r = (double*)(d.region + L.r); a.p = (double*)(d.region + L.p); a.kp = (double*)(d.region + L.kp);
+    a.Minv = (double*)(d.region + L.Minv);
+    a.ctrl = (Ctrl*)(d.region + L.ctrl);
+    a.part_m = d.part_m.p;
+    a.part_n = d.part_uni.p;
+  }
   return a;
 }
 
-// one launch of the persistent kernel; fills w->h_out and device-timed milliseconds
-void run_admm(b200qp_solver* sv, const KArgs& a, float* ms) {
+typedef void (*admm_dist_fn)(const KArgs, const XArgs);
+admm_dist_fn pick_kernel_dist(int lgn, int lgm) {
+#define CASE(a, b) if (lgn == a && lgm == b) return admm_kernel_dist<a, b>;
+  CASE(4, 4) CASE(4, 8) CASE(4, 32) CASE(8, 4) CASE(8, 8) CASE(8, 32) CASE(32, 4) CASE(32, 8) CASE(32, 32)
+#undef CASE
+  return admm_kernel_dist<8, 8>;
+}
+
+XArgs make_xargs(Work* w) {
+  XArgs x{};
+  Work::Dist& d = w->dist;
+  RegionLayout L(w->n);
+  x.rank = d.rank; x.world = d.world;
+  for (int h = 0; h <= d.world; ++h) x.slice[h] = d.slice[h];
+  for (int h = 0; h < d.world; ++h) {
+    char* b = d.peer[h];
+    x.part_w[h] = (double*)(b + L.part_w); x.part_y[h] = (double*)(b + L.part_y);
+    x.r[h] = (double*)(b + L.r); x.p[h] = (double*)(b + L.p); x.kp[h] = (double*)(b + L.kp);
+    x.Minv[h] = (double*)(b + L.Minv);
+    x.flags[h] = (unsigned long long*)(b + L.flags);
+    x.payload[h] = (double*)(b + L.payload);
+    x.abort_flag[h] = &((Ctrl*)(b + L.ctrl))->abort;
+  }
+  x.sum_w = d.sum_w.p; x.sum_y = d.sum_y.p; x.xtot = d.xtot.p; x.release = d.release.p;
+  x.part_nfull = d.part_nfull.p; x.part_slice = d.part_slice.p; x.part_uni = d.part_uni.p;
+  x.xepoch0 = d.xepoch;
+  return x;
+}
+
+// launch of the persistent kernel (asynchronous); finish_admm() waits and fills w->h_out + device time
+void launch_admm(b200qp_solver* sv, const KArgs& a) {
   Work* w = W(sv);
-  CK(cudaMemsetAsync(w->ctrl.p, 0, sizeof(Ctrl), w->stream));
+  CK(cudaMemsetAsync(a.ctrl, 0, sizeof(Ctrl), w->stream));
   CK(cudaMemsetAsync(w->out.p, 0, sizeof(KOut), w->stream));
-  admm_fn fn = pick_kernel(w->lgn, w->lgm);
-  void* params[] = {(void*)&a};
-  CK(cudaEventRecord(w->ev0, w->stream));
-  CK(cudaLaunchCooperativeKernel((const void*)fn, dim3(w->G), dim3(NT), params, 0, w->stream));
+  if (w->dist.world > 1 || w->dist.connected) {
+    if (!w->dist.connected || w->dist.broken) throw (int)B200QP_WORKSPACE_NOT_INIT_ERROR;
+    CK(cudaMemsetAsync(w->dist.release.p, 0, sizeof(unsigned long long), w->stream));
+    XArgs x = make_xargs(w);
+    admm_dist_fn fn = pick_kernel_dist(w->dist.lgn, w->dist.lgm);
+    void* params[] = {(void*)&a, (void*)&x};
+    CK(cudaEventRecord(w->ev0, w->stream));
+    CK(cudaLaunchCooperativeKernel((const void*)fn, dim3(w->dist.G), dim3(NT), params, 0, w->stream));
+  } else {
+    admm_fn fn = pick_kernel(w->lgn, w->lgm);
+    void* params[] = {(void*)&a};
+    CK(cudaEventRecord(w->ev0, w->stream));
+    CK(cudaLaunchCooperativeKernel((const void*)fn, dim3(w->G), dim3(NT), params, 0, w->stream));
+  }
   CK(cudaEventRecord(w->ev1, w->stream));
-  CK(cudaMemcpyAsync(&w->h_out, w->out.p, sizeof(KOut), cudaMemcpyDeviceToHost, w->stream));
+  // nothing host-blocking may follow here: in a multi-rank group the other ranks are launched next
+}
+void finish_admm(b200qp_solver* sv, float* ms) {
+  Work* w = W(sv);
   CK(cudaStreamSynchronize(w->stream));
+  CK(cudaMemcpy(&w->h_out, w->out.p, sizeof(KOut), cudaMemcpyDeviceToHost));
   CK(cudaEventElapsedTime(ms, w->ev0, w->ev1));
+  if (w->dist.connected) {
+    if (w->h_out.aborted || w->h_out.status == 0) w->dist.broken = true;
+    else w->dist.xepoch = (unsigned long long)w->h_out.xepoch;
+  }
+}
+void run_admm(b200qp_solver* sv, const KArgs& a, float* ms) {
+  launch_admm(sv, a);
+  finish_admm(sv, ms);
 }
 
 // algorithmic HBM bytes of one solve (DESIGN.md "byte model"), from the kernel's own counters
@@ -590,22 +701,38 @@ void b200qp_cold_start(b200qp_solver* solver) {
   w->x.zero(w->stream); w->z.zero(w->stream); w->y.zero(w->stream);
 }
 
-b200qp_int b200qp_solve(b200qp_solver* solver) {
+static b200qp_int solve_begin(b200qp_solver* solver) {
   if (!solver || !solver->work) return B200QP_WORKSPACE_NOT_INIT_ERROR;
   Work* w = W(solver);
   b200qp_settings* st = solver->settings;
-  b200qp_info* info = solver->info;
-  const double t0 = now_s();
+  w->t_solve_begin = now_s();
   try {
     CK(cudaSetDevice(w->device));
-    if (w->clear_update_time) info->update_time = 0.0;
+    if (w->clear_update_time) solver->info->update_time = 0.0;
     if (!st->warm_starting) b200qp_cold_start(solver);      // reference: _osqp.py:1203-1205
     KArgs a = make_args(solver);
+    launch_admm(solver, a);
+    w->in_flight = true;
+  } catch (int code) {
+    return code;
+  }
+  return 0;
+}
+
+static b200qp_int solve_end(b200qp_solver* solver) {
+  Work* w = W(solver);
+  b200qp_settings* st = solver->settings;
+  b200qp_info* info = solver->info;
+  const double t0 = w->t_solve_begin;
+  if (!w->in_flight) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  w->in_flight = false;
+  try {
+    CK(cudaSetDevice(w->device));
     float ms = 0.f;
-    run_admm(solver, a, &ms);
+    finish_admm(solver, &ms);
     const KOut& o = w->h_out;
     if (o.aborted || o.status == 0) {
-      std::fprintf(stderr, "[b200qp] ADMM kernel aborted (grid barrier watchdog)\n");
+      std::fprintf(stderr, "[b200qp] ADMM kernel aborted (grid / cross-GPU barrier watchdog)\n");
       return B200QP_WORKSPACE_NOT_INIT_ERROR;
     }
     st->rho = o.rho;
@@ -625,9 +752,10 @@ b200qp_int b200qp_solve(b200qp_solver* solver) {
     w->stats.admm_iters = o.iter; w->stats.cg_iters = o.cg_iters; w->stats.grid_barriers = o.barriers;
     w->stats.kernel_ms = ms;
     w->stats.algo_bytes = algo_bytes(w, o.iter, o.cg_iters, st->check_termination);
+    if (w->dist.connected) { w->stats.grid = w->dist.G; }
     info->solve_time = now_s() - t0;
 
-    if (st->verbose) {
+    if (st->verbose && w->dist.rank == 0) {
       std::vector<LogRow> rows(std::min(o.log_rows, w->log_cap));
       if (!rows.empty())
         CK(cudaMemcpy(rows.data(), w->log.p, rows.size() * sizeof(LogRow), cudaMemcpyDeviceToHost));
@@ -638,15 +766,16 @@ b200qp_int b200qp_solve(b200qp_solver* solver) {
                       rows[i].dual_res, rows[i].rho, rows[i].t_ms * 1e-3);
     }
 
-    // polish (reference: _osqp.py:1277-1281) -- see polish.cuh
+    // polish (reference: _osqp.py:1277-1281); single-GPU solver only
     info->polish_time = 0.0;
-    if (st->polishing && o.status == B200QP_SOLVED) {
+    if (st->polishing && o.status == B200QP_SOLVED && !w->dist.connected) {
       const double tp = now_s();
       polish_impl(solver);
       info->polish_time = now_s() - tp;
     }
 
-    // solution / certificates (reference: _osqp.py:1098-1115)
+    // solution / certificates (reference: _osqp.py:1098-1115).  Multi-GPU: x is replicated, y / the primal
+    // certificate are valid on this rank's row slab [mlo, mhi) only (b200qp_dist_row_range).
     const int mode = (o.status == B200QP_PRIMAL_INFEASIBLE || o.status == B200QP_PRIMAL_INFEASIBLE_INACCURATE) ? 1
                    : (o.status == B200QP_DUAL_INFEASIBLE || o.status == B200QP_DUAL_INFEASIBLE_INACCURATE) ? 2 : 0;
     const int n = w->n, m = w->m;
@@ -662,7 +791,7 @@ b200qp_int b200qp_solve(b200qp_solver* solver) {
     info->run_time = (w->first_run ? info->setup_time : info->update_time) + info->solve_time + info->polish_time;
     w->first_run = false;
     w->clear_update_time = true;
-    if (st->verbose) {
+    if (st->verbose && w->dist.rank == 0) {
       std::printf("\nstatus:               %s\n", info->status);
       if (st->polishing && o.status == B200QP_SOLVED)
         std::printf("solution polish:      %s\n", info->status_polish == 1 ? "successful" : "unsuccessful");
@@ -677,6 +806,12 @@ b200qp_int b200qp_solve(b200qp_solver* solver) {
     return code;
   }
   return 0;
+}
+
+b200qp_int b200qp_solve(b200qp_solver* solver) {
+  const b200qp_int rc = solve_begin(solver);
+  if (rc) return rc;
+  return solve_end(solver);
 }
 
 b200qp_int b200qp_get_stats(const b200qp_solver* solver, b200qp_stats* stats) {
@@ -829,6 +964,189 @@ b200qp_int b200qp_update_settings(b200qp_solver* solver, const b200qp_settings* 
   *st = t;
   if (precond_changed) return b200qp_update_rho(solver, st->rho);
   return 0;
+}
+
+
+// ================================================================== multi-GPU: one QP, row-partitioned
+// (SURVEY.md 8e config 4).  Every rank receives the full problem, runs the ordinary setup on its own
+// GPU (equilibration needs global column norms anyway), then keeps a row slab of A / A' and joins the
+// other ranks through one peer-mapped "shared region" per rank (cudaIpc between processes, direct
+// pointers inside one process).  The data path has no host step and no NCCL call: the exchange is
+// fused into the persistent kernel (admm_kernel_dist.cuh).
+
+static int dist_grid(Work* w, int share) {
+  const long long work = (long long)w->P.nnz + 2LL * w->A.nnz / std::max(1, w->dist.world) + 4LL * (w->n + w->m);
+  long long want = work / 8192;
+  if (const char* e = std::getenv("B200QP_GRID")) want = std::atoll(e);
+  const int cap = std::max(1, w->max_coop_dist / std::max(1, share));
+  return (int)std::min<long long>(std::max<long long>(want, 1), cap);
+}
+
+b200qp_int b200qp_dist_setup(b200qp_solver** solverp, b200qp_int rank, b200qp_int world, b200qp_int ranks_on_device,
+                             const b200qp_csc* P, const b200qp_float* q, const b200qp_csc* A, const b200qp_float* l,
+                             const b200qp_float* u, b200qp_int m, b200qp_int n, const b200qp_settings* settings) {
+  if (world < 1 || world > MAXW || rank < 0 || rank >= world) return B200QP_DATA_VALIDATION_ERROR;
+  b200qp_settings st = *settings;
+  if (rank != 0) st.verbose = 0;
+  int err = b200qp_setup(solverp, P, q, A, l, u, m, n, &st);
+  if (err) return err;
+  b200qp_solver* sv = *solverp;
+  Work* w = W(sv);
+  Work::Dist& d = w->dist;
+  try {
+    CK(cudaSetDevice(w->device));
+    cudaStream_t s = w->stream;
+    d.rank = rank; d.world = world;
+    // row slabs balanced by nnz(A); variable slices balanced by nnz(P) -- same on every rank
+    std::vector<int> rows, sl;
+    make_partition(m, world, {&w->A.h_ptr}, rows);
+    make_partition(n, world, {&w->P.h_ptr}, sl);
+    d.mlo = rows[rank]; d.mhi = rows[rank + 1];
+    for (int h = 0; h <= world; ++h) d.slice[h] = sl[h];
+    const int mlo = d.mlo, mhi = d.mhi, mg = mhi - mlo;
+    // compact A_g' from the (scaled) CSR(A') = CSC(A) arrays: keep row indices in [mlo, mhi)
+    const int nnzA = w->A.nnz;
+    std::vector<double> atx(nnzA);
+    if (nnzA) CK(cudaMemcpyAsync(atx.data(), w->At.val.p, (size_t)nnzA * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<int> gp(n + 1, 0), gi;
+    std::vector<double> gx;
+    for (int j = 0; j < n; ++j) {
+      for (int k = A->p[j]; k < A->p[j + 1]; ++k) {
+        const int i = A->i[k];
+        if (i >= mlo && i < mhi) { gi.push_back(i - mlo); gx.push_back(atx[k]); }
+      }
+      gp[j + 1] = (int)gi.size();
+    }
+    d.Atg.upload(n, std::max(mg, 1), gp, gi, gx, s);
+    // shared region
+    RegionLayout L(n);
+    d.region_bytes = L.total;
+    CK(cudaMalloc(&d.region, L.total));
+    CK(cudaMemsetAsync(d.region, 0, L.total, s));
+    CK(cudaMemcpyAsync(d.region + L.Minv, w->Minv.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    w->Minv.borrow((double*)(d.region + L.Minv), n);     // later Jacobi refreshes land in the shared copy
+    d.peer[rank] = d.region;
+    d.sum_w.alloc(n); d.sum_y.alloc(n); d.xtot.alloc(2 * KMAX); d.release.alloc(1);
+    d.sum_w.zero(s); d.sum_y.zero(s); d.xtot.zero(s); d.release.zero(s);
+    // launch geometry (identical on all ranks: the replicated reductions must agree bit for bit)
+    d.lgn = pick_lg(n ? (double)(w->P.nnz / world + d.Atg.nnz) / n : 1.0);
+    d.lgn = pick_lg(n ? (double)(w->P.nnz + w->A.nnz) / n / 2 : 1.0);
+    d.lgm = w->lgm;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)pick_kernel_dist(d.lgn, d.lgm), NT, 0));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, w->device));
+    if (occ < 1) throw (int)B200QP_ALGEBRA_LOAD_ERROR;
+    w->max_coop_dist = occ * prop.multiProcessorCount;
+    d.G = dist_grid(w, std::max(1, (int)ranks_on_device));
+    std::vector<int> pm, pf, ps, pu(d.G + 1);
+    {   // local rows of A_g: weights from the global row pointer, shifted
+      std::vector<int> lp(mg + 1);
+      for (int i = 0; i <= mg; ++i) lp[i] = w->A.h_ptr[mlo + i] - w->A.h_ptr[mlo];
+      make_partition(mg, d.G, {&lp}, pm);
+    }
+    make_partition(n, d.G, {&d.Atg.h_ptr}, pf);
+    {   // my slice by nnz(P): partition the sub-range, then shift to absolute row numbers
+      const int a0 = d.slice[rank], a1 = d.slice[rank + 1];
+      std::vector<int> lp(a1 - a0 + 1);
+      for (int i = 0; i <= a1 - a0; ++i) lp[i] = w->P.h_ptr[a0 + i] - w->P.h_ptr[a0];
+      make_partition(a1 - a0, d.G, {&lp}, ps);
+      for (int& v : ps) v += a0;
+    }
+    for (int g = 0; g <= d.G; ++g) pu[g] = (int)((long long)n * g / d.G);
+    d.part_m.alloc(d.G + 1); d.part_m.upload(pm.data(), d.G + 1, s);
+    d.part_nfull.alloc(d.G + 1); d.part_nfull.upload(pf.data(), d.G + 1, s);
+    d.part_slice.alloc(d.G + 1); d.part_slice.upload(ps.data(), d.G + 1, s);
+    d.part_uni.alloc(d.G + 1); d.part_uni.upload(pu.data(), d.G + 1, s);
+    w->red.alloc((size_t)2 * KMAX * std::max(d.G, w->G)); w->red.zero(s);
+    CK(cudaStreamSynchronize(s));
+    if (world == 1) d.connected = true;
+  } catch (int code) {
+    b200qp_cleanup(sv);
+    *solverp = nullptr;
+    return code;
+  }
+  return 0;
+}
+
+b200qp_int b200qp_dist_row_range(const b200qp_solver* solver, b200qp_int* mlo, b200qp_int* mhi) {
+  if (!solver || !solver->work) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  const Work* w = W(solver);
+  if (mlo) *mlo = w->dist.region ? w->dist.mlo : 0;
+  if (mhi) *mhi = w->dist.region ? w->dist.mhi : w->m;
+  return 0;
+}
+
+b200qp_int b200qp_dist_get_handle(b200qp_solver* solver, void* handle64) {
+  if (!solver || !solver->work || !W(solver)->dist.region || !handle64) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  Work* w = W(solver);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  try {
+    CK(cudaSetDevice(w->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, w->dist.region));
+    std::memcpy(handle64, &h, 64);
+  } catch (int code) { return code; }
+  return 0;
+}
+
+// multi-process: handles = world x 64 bytes, in rank order (exchanged by the caller, e.g. torch.distributed)
+b200qp_int b200qp_dist_connect_ipc(b200qp_solver* solver, const void* handles) {
+  if (!solver || !solver->work || !W(solver)->dist.region || !handles) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  Work* w = W(solver);
+  Work::Dist& d = w->dist;
+  try {
+    CK(cudaSetDevice(w->device));
+    for (int h = 0; h < d.world; ++h) {
+      if (h == d.rank) continue;
+      cudaIpcMemHandle_t mh;
+      std::memcpy(&mh, (const char*)handles + 64 * h, 64);
+      void* ptr = nullptr;
+      CK(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+      d.peer[h] = (char*)ptr;
+      d.opened[h] = true;
+    }
+    d.connected = true;
+  } catch (int code) { return code; }
+  return 0;
+}
+
+// single process driving all ranks (one device per rank, or several ranks sharing a device for tests)
+b200qp_int b200qp_dist_connect_local(b200qp_solver** group, b200qp_int world) {
+  if (!group || world < 1 || world > MAXW) return B200QP_DATA_VALIDATION_ERROR;
+  try {
+    for (int a = 0; a < world; ++a) {
+      if (!group[a] || !group[a]->work || !W(group[a])->dist.region) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+      Work* wa = W(group[a]);
+      if (wa->dist.world != world || wa->dist.rank != a) return B200QP_DATA_VALIDATION_ERROR;
+      CK(cudaSetDevice(wa->device));
+      for (int b = 0; b < world; ++b) {
+        Work* wb = W(group[b]);
+        if (wb->device != wa->device) {
+          int can = 0;
+          CK(cudaDeviceCanAccessPeer(&can, wa->device, wb->device));
+          if (!can) return B200QP_ALGEBRA_LOAD_ERROR;
+          cudaError_t e = cudaDeviceEnablePeerAccess(wb->device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+          cudaGetLastError();
+        }
+        wa->dist.peer[b] = wb->dist.region;
+      }
+      wa->dist.connected = true;
+    }
+  } catch (int code) { return code; }
+  return 0;
+}
+
+b200qp_int b200qp_dist_solve_group(b200qp_solver** group, b200qp_int world) {
+  if (!group || world < 1 || world > MAXW) return B200QP_DATA_VALIDATION_ERROR;
+  b200qp_int rc = 0;
+  int launched = 0;
+  for (int a = 0; a < world && !rc; ++a) { rc = solve_begin(group[a]); if (!rc) launched++; }
+  for (int a = 0; a < launched; ++a) { const b200qp_int r2 = solve_end(group[a]); if (!rc) rc = r2; }
+  return rc;
 }
 
 // ---------------------------------------------------------------------------- standalone SpMV

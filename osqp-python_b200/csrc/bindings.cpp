@@ -8,6 +8,8 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <vector>
+#include <cstring>
 
 #include "../../include/b200qp.h"
 
@@ -77,14 +79,17 @@ class Solver {
  public:
   Solver(const CscHandle& P, const py::array_t<b200qp_float>& q, const CscHandle& A,
          const py::array_t<b200qp_float>& l, const py::array_t<b200qp_float>& u, b200qp_int m, b200qp_int n,
-         const b200qp_settings* settings)
+         const b200qp_settings* settings, b200qp_int rank = 0, b200qp_int world = 0, b200qp_int ranks_on_device = 1)
       : m_(m), n_(n) {
     darray qc = darray::ensure(q), lc = darray::ensure(l), uc = darray::ensure(u);
     if (qc.size() != n || lc.size() != m || uc.size() != m) throw py::value_error(std::to_string(B200QP_DATA_VALIDATION_ERROR));
     b200qp_int status;
     {
       py::gil_scoped_release nogil;
-      status = b200qp_setup(&s_, &P.view, qc.data(), &A.view, lc.data(), uc.data(), m, n, settings);
+      if (world >= 1)   // multi-GPU rank of a row-partitioned QP (world == 0: the reference's single-GPU solver)
+        status = b200qp_dist_setup(&s_, rank, world, ranks_on_device, &P.view, qc.data(), &A.view, lc.data(), uc.data(), m, n, settings);
+      else
+        status = b200qp_setup(&s_, &P.view, qc.data(), &A.view, lc.data(), uc.data(), m, n, settings);
     }
     // nonzero status -> ValueError(str(code)); the facade turns it into OSQPException (interface.py:128-141)
     if (status) throw py::value_error(std::to_string(status));
@@ -132,6 +137,22 @@ class Solver {
   b200qp_settings* settings() { return s_->settings; }
   b200qp_info* info() { return s_->info; }
   SolutionView& solution() { return sol_; }
+  b200qp_solver* raw() const { return s_; }
+  py::bytes dist_handle() {
+    char h[64];
+    const b200qp_int rc = b200qp_dist_get_handle(s_, h);
+    if (rc) throw py::value_error(std::to_string(rc));
+    return py::bytes(h, 64);
+  }
+  void dist_connect_ipc(const std::string& handles) {
+    const b200qp_int rc = b200qp_dist_connect_ipc(s_, handles.data());
+    if (rc) throw py::value_error(std::to_string(rc));
+  }
+  py::tuple dist_row_range() const {
+    b200qp_int lo = 0, hi = 0;
+    b200qp_dist_row_range(s_, &lo, &hi);
+    return py::make_tuple(lo, hi);
+  }
   py::dict stats() const {
     b200qp_stats st{};
     b200qp_get_stats(s_, &st);
@@ -278,8 +299,12 @@ PYBIND11_MODULE(osqp_cuda, mod) {
   py::class_<Solver>(mod, "OSQPSolver", py::module_local())
       .def(py::init<const CscHandle&, const py::array_t<b200qp_float>&, const CscHandle&,
                     const py::array_t<b200qp_float>&, const py::array_t<b200qp_float>&, b200qp_int, b200qp_int,
-                    const b200qp_settings*>(),
-           "P"_a, "q"_a.noconvert(), "A"_a, "l"_a.noconvert(), "u"_a.noconvert(), "m"_a, "n"_a, "settings"_a)
+                    const b200qp_settings*, b200qp_int, b200qp_int, b200qp_int>(),
+           "P"_a, "q"_a.noconvert(), "A"_a, "l"_a.noconvert(), "u"_a.noconvert(), "m"_a, "n"_a, "settings"_a,
+           "rank"_a = 0, "world"_a = 0, "ranks_on_device"_a = 1)
+      .def("dist_handle", &Solver::dist_handle)
+      .def("dist_connect_ipc", &Solver::dist_connect_ipc)
+      .def("dist_row_range", &Solver::dist_row_range)
       .def_property_readonly("solution", &Solver::solution, py::return_value_policy::reference_internal)
       .def_property_readonly("info", &Solver::info, py::return_value_policy::reference_internal)
       .def("warm_start", &Solver::warm_start, "x"_a.none(true), "y"_a.none(true))
@@ -291,4 +316,22 @@ PYBIND11_MODULE(osqp_cuda, mod) {
       .def("update_rho", &Solver::update_rho)
       .def("get_settings", &Solver::settings, py::return_value_policy::reference_internal)
       .def("get_stats", &Solver::stats);
+
+  // one process driving every rank of a row-partitioned QP (include/b200qp.h: b200qp_dist_*)
+  mod.def("dist_connect_local", [](py::list solvers) {
+    std::vector<b200qp_solver*> grp;
+    for (auto h : solvers) grp.push_back(h.cast<Solver&>().raw());
+    const b200qp_int rc = b200qp_dist_connect_local(grp.data(), (b200qp_int)grp.size());
+    if (rc) throw py::value_error(std::to_string(rc));
+  });
+  mod.def("dist_solve_group", [](py::list solvers) {
+    std::vector<b200qp_solver*> grp;
+    for (auto h : solvers) grp.push_back(h.cast<Solver&>().raw());
+    b200qp_int rc;
+    {
+      py::gil_scoped_release nogil;
+      rc = b200qp_dist_solve_group(grp.data(), (b200qp_int)grp.size());
+    }
+    return rc;
+  });
 }
