@@ -222,6 +222,7 @@ def run_ours(args):
     sampler.start()
     dev_ms, wall_ms, iters, cg, bytes_algo, launches = 0.0, 0.0, 0, 0, 0.0, 0
     status = None
+    phases = [0.0] * 8
     for i in range(args.steps):
         t0 = time.perf_counter()
         prob.update(q=q_host[i & 1])                 # H2D 8n bytes
@@ -229,6 +230,7 @@ def run_ours(args):
         wall_ms += 1e3 * (time.perf_counter() - t0)
         st = prob.stats()
         dev_ms += st["kernel_ms"]; iters += st["admm_iters"]; cg += st["cg_iters"]; bytes_algo += st["algo_bytes"]
+        phases = [a + b for a, b in zip(phases, st["phase_ms"])]
         launches += 1 + 3 + 2                        # ADMM kernel; q-update (scale + 2 norm kernels); store x / y
         status = res.info.status
     clocks = sampler.stop()
@@ -242,6 +244,8 @@ def run_ours(args):
         "config": {"workload": workload_name(), "admm_iters_per_step": iters // args.steps,
                    "pcg_iters_per_admm_iter": cg / max(iters, 1), "status": status, "l2": "inputs larger than L2 "
                    "(working set ~0.45 GB vs 126 MB L2); no flush between steps",
+                   "phase_ms_per_step": dict(zip(["R", "C1_Ap", "C2_Kp", "C3_axpy_dots", "C4_p", "Z", "x6", "x7"],
+                                                 [round(v / args.steps, 3) for v in phases])),
                    "grid": f"{st['grid']}x{st['block']}", "setup_s": t_setup, "problem_gen_s": t_gen,
                    "settings": {k: v for k, v in SOLVE_KW.items()}},
         "roofline": {"bound": "hbm", "kernel": "b200qp::admm_kernel (persistent, one launch per solve)",

@@ -174,6 +174,7 @@ typedef struct {
   double algo_bytes;      /* algorithmic HBM bytes of that launch (DESIGN.md byte model) */
   b200qp_int grid, block; /* launch shape                                               */
   b200qp_int n, m, nnzP_full, nnzA;
+  double phase_ms[8];     /* device time per phase kind (R, C1, C2, C3, C4, Z, -, -), measured on CTA 0 */
 } b200qp_stats;
 
 /* ---- the reference path ------------------------------------------------------------------ */

@@ -26,6 +26,7 @@ struct KOut {                 // written by CTA 0 at kernel exit, read back by t
   long long cg_iters; long long barriers;
   double obj, dual_obj, gap, prim_res, dual_res, rho_estimate, rho, rel_kkt;
   int log_rows; int pad;
+  long long phase_ns[8];      // CTA-0 time per phase kind: R, C1, C2, C3, C4, Z, other (barrier waits included)
   long long xepoch;           // multi-GPU kernel: cross-GPU barriers completed (carried to the next launch)
 };
 
@@ -57,15 +58,53 @@ struct KArgs {
   int polish_mode;
 };
 
-// dot of one CSR row with a vector; LG lanes cooperate, partial sums returned per lane
+// dot of one CSR row with a vector; LG lanes cooperate, partial sums returned per lane.
+// The first two entries of every lane are fetched in straight-line code so that the index loads, then
+// the gathers, of both entries (and of the other rows the caller interleaves) are in flight together.
 template <int LG>
 __device__ __forceinline__ double row_dot(const CsrMat& M, const double* xv, int row, bool valid, int lane) {
   double acc = 0.0;
   if (valid) {
     const int a = __ldg(M.ptr + row), b = __ldg(M.ptr + row + 1);
-    for (int k = a + lane; k < b; k += LG) acc = fma(ld_stream(M.val + k), ld_vec(xv + ld_stream(M.idx + k)), acc);
+    const int k0 = a + lane, k1 = k0 + LG;
+    const bool h0 = k0 < b, h1 = k1 < b;
+    int j0 = 0, j1 = 0;
+    double v0 = 0.0, v1 = 0.0;
+    if (h0) { j0 = ld_stream(M.idx + k0); v0 = ld_stream(M.val + k0); }
+    if (h1) { j1 = ld_stream(M.idx + k1); v1 = ld_stream(M.val + k1); }
+    double x0 = 0.0, x1 = 0.0;
+    if (h0) x0 = ld_vec(xv + j0);
+    if (h1) x1 = ld_vec(xv + j1);
+    acc = fma(v1, x1, v0 * x0);
+    for (int k = k1 + LG; k < b; k += LG) acc = fma(ld_stream(M.val + k), ld_vec(xv + ld_stream(M.idx + k)), acc);
   }
   return acc;
+}
+// two independent row dots (different rows of one matrix, or one row of two matrices) with their loads
+// interleaved: 4 index loads, then 4 gathers in flight per lane before the first FMA.
+template <int LG>
+__device__ __forceinline__ void dot_pair(const CsrMat& M1, const double* x1, int row1, bool ok1, const CsrMat& M2,
+                                         const double* x2, int row2, bool ok2, int lane, double& acc1, double& acc2) {
+  int a1 = 0, b1 = 0, a2 = 0, b2 = 0;
+  if (ok1) { a1 = __ldg(M1.ptr + row1); b1 = __ldg(M1.ptr + row1 + 1); }
+  if (ok2) { a2 = __ldg(M2.ptr + row2); b2 = __ldg(M2.ptr + row2 + 1); }
+  const int k10 = a1 + lane, k11 = k10 + LG, k20 = a2 + lane, k21 = k20 + LG;
+  const bool h10 = k10 < b1, h11 = k11 < b1, h20 = k20 < b2, h21 = k21 < b2;
+  int j10 = 0, j11 = 0, j20 = 0, j21 = 0;
+  double v10 = 0.0, v11 = 0.0, v20 = 0.0, v21 = 0.0;
+  if (h10) { j10 = ld_stream(M1.idx + k10); v10 = ld_stream(M1.val + k10); }
+  if (h20) { j20 = ld_stream(M2.idx + k20); v20 = ld_stream(M2.val + k20); }
+  if (h11) { j11 = ld_stream(M1.idx + k11); v11 = ld_stream(M1.val + k11); }
+  if (h21) { j21 = ld_stream(M2.idx + k21); v21 = ld_stream(M2.val + k21); }
+  double y10 = 0.0, y11 = 0.0, y20 = 0.0, y21 = 0.0;
+  if (h10) y10 = ld_vec(x1 + j10);
+  if (h20) y20 = ld_vec(x2 + j20);
+  if (h11) y11 = ld_vec(x1 + j11);
+  if (h21) y21 = ld_vec(x2 + j21);
+  acc1 = fma(v11, y11, v10 * y10);
+  acc2 = fma(v21, y21, v20 * y20);
+  for (int k = k11 + LG; k < b1; k += LG) acc1 = fma(ld_stream(M1.val + k), ld_vec(x1 + ld_stream(M1.idx + k)), acc1);
+  for (int k = k21 + LG; k < b2; k += LG) acc2 = fma(ld_stream(M2.val + k), ld_vec(x2 + ld_stream(M2.idx + k)), acc2);
 }
 template <int LG>
 __device__ __forceinline__ void row_dot2(const CsrMat& M, const double* x1, const double* x2, int row, bool valid,
@@ -162,6 +201,14 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
   }
   B200QP_BARRIER_OR_DIE();
 
+  // per-phase timing (CTA 0 only; a few globaltimer reads per phase)
+  __shared__ long long t_phase[8];
+  __shared__ unsigned long long t_mark;
+  if (tid == 0) { for (int i = 0; i < 8; ++i) t_phase[i] = 0; t_mark = global_timer_ns(); }
+  auto mark = [&](int id) {
+    if (cta == 0 && tid == 0) { const unsigned long long now = global_timer_ns(); t_phase[id] += (long long)(now - t_mark); t_mark = now; }
+  };
+
   // R phase body (full = with the residual quantities of the current iterate)
   auto phase_R = [&](bool full, bool lite) {
     // lite: px already stored, recompute only A'w2 (after a rho update); also refreshes Minv
@@ -177,9 +224,12 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
         if (a.cg_precond) msum = row_dot_sq<LGN>(a.At, a.rho_v, row, valid, lane_n);
         msum = group_sum<LGN>(msum);
       } else {
-        px = row_dot<LGN>(a.P, a.x, row, valid, lane_n);
-        if (full) row_dot2<LGN>(a.At, a.w2, a.y, row, valid, lane_n, atw, aty);
-        else atw = row_dot<LGN>(a.At, a.w2, row, valid, lane_n);
+        if (full) {
+          px = row_dot<LGN>(a.P, a.x, row, valid, lane_n);
+          row_dot2<LGN>(a.At, a.w2, a.y, row, valid, lane_n, atw, aty);
+        } else {
+          dot_pair<LGN>(a.P, a.x, row, valid, a.At, a.w2, row, valid, lane_n, px, atw);
+        }
         px = group_sum<LGN>(px);
         if (full) aty = group_sum<LGN>(aty);
       }
@@ -299,6 +349,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
       const double* bk = phase_R(full, false);
       B200QP_BARRIER_OR_DIE();
       load_R(bk, full);
+      mark(0);
     }
     if (full && a.verbose && cta == 0 && tid == 0 && chk) {
       const int row = (k / (a.check_term > 0 ? a.check_term : 1)) - 1;
@@ -348,20 +399,28 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
       const double tol = a.cg_tol_frac * r0max;
       for (int j = 0; j < a.cg_max_iter; ++j) {
         // C1: w = rho .* (A p)
-        for (int base = m0; base < m1; base += NGM) {
-          const int row = base + grp_m;
-          const bool valid = row < m1;
-          const double acc = group_sum<LGM>(row_dot<LGM>(a.A, a.p, row, valid, lane_m));
-          if (valid && lane_m == 0) a.w[row] = a.rho_v[row] * acc;
+        for (int base = m0; base < m1; base += 2 * NGM) {
+          const int rowA = base + grp_m, rowB = rowA + NGM;
+          const bool okA = rowA < m1, okB = rowB < m1;
+          double accA, accB;
+          dot_pair<LGM>(a.A, a.p, rowA, okA, a.A, a.p, rowB, okB, lane_m, accA, accB);
+          accA = group_sum<LGM>(accA);
+          accB = group_sum<LGM>(accB);
+          if (lane_m == 0) {
+            if (okA) a.w[rowA] = a.rho_v[rowA] * accA;
+            if (okB) a.w[rowB] = a.rho_v[rowB] * accB;
+          }
         }
         B200QP_BARRIER_OR_DIE();
+        mark(1);
         // C2: kp = P p + sigma p + A' w ; <p, kp>
         double v1[1] = {0.0};
         for (int base = n0; base < n1; base += NGN) {
           const int row = base + grp_n;
           const bool valid = row < n1;
-          double acc = row_dot<LGN>(a.P, a.p, row, valid, lane_n) + row_dot<LGN>(a.At, a.w, row, valid, lane_n);
-          acc = group_sum<LGN>(acc);
+          double accP, accA;
+          dot_pair<LGN>(a.P, a.p, row, valid, a.At, a.w, row, valid, lane_n, accP, accA);
+          const double acc = group_sum<LGN>(accP + accA);
           if (valid && lane_n == 0) {
             const double pj = a.p[row];
             const double kpj = acc + sigma * pj;
@@ -373,6 +432,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
         block_reduce_store<1>(v1, 0u, bk, G, s_red);
         B200QP_BARRIER_OR_DIE();
         grid_reduce_load<1>(bk, G, 0u, s_tot);
+        mark(2);
         const double pkp = s_tot[0];
         if (!(pkp > 0.0)) { status = 9; break; }   // K not positive definite (or NaN): non-convex
         const double aj = rz / pkp;
@@ -392,6 +452,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
         block_reduce_store<2>(v2, 2u, bk, G, s_red);
         B200QP_BARRIER_OR_DIE();
         grid_reduce_load<2>(bk, G, 2u, s_tot);
+        mark(3);
         const double rz_new = s_tot[0], rmax = s_tot[1];
         if (!(rmax > tol) || j + 1 == a.cg_max_iter) break;
         // C4: p = Minv r + b p
@@ -399,6 +460,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
         rz = rz_new;
         for (int i = n0 + tid; i < n1; i += NT) a.p[i] = fma(bj, a.p[i], a.Minv[i] * a.r[i]);
         B200QP_BARRIER_OR_DIE();
+        mark(4);
       }
       if (status) break;
     }
@@ -417,11 +479,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
 #pragma unroll
       for (int i = 0; i < Z_K; ++i) v[i] = 0.0;
       v[Z_VU] = NEG_INF; v[Z_VL] = NEG_INF;
-      for (int base = m0; base < m1; base += NGM) {
-        const int row = base + grp_m;
-        const bool valid = row < m1;
-        const double ad = group_sum<LGM>(row_dot<LGM>(a.A, a.d, row, valid, lane_m));
-        if (valid && lane_m == 0) {
+      auto z_row = [&](int row, double ad) {
           const double ax_old = a.ax[row], z_old = a.z[row], y_old = a.y[row];
           const double rv = a.rho_v[row], ri = a.rho_inv[row], li = a.l[row], ui = a.u[row];
           const double zt = ax_old + ad;                                   // z~ = A x~
@@ -458,6 +516,17 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
             // support function for the dual objective
             v[Z_SUP] += (ufin ? ui * fmax(yn, 0.0) : 0.0) + (lfin ? li * fmin(yn, 0.0) : 0.0);
           }
+      };
+      for (int base = m0; base < m1; base += 2 * NGM) {
+        const int rowA = base + grp_m, rowB = rowA + NGM;
+        const bool okA = rowA < m1, okB = rowB < m1;
+        double adA, adB;
+        dot_pair<LGM>(a.A, a.d, rowA, okA, a.A, a.d, rowB, okB, lane_m, adA, adB);
+        adA = group_sum<LGM>(adA);
+        adB = group_sum<LGM>(adB);
+        if (lane_m == 0) {
+          if (okA) z_row(rowA, adA);
+          if (okB) z_row(rowB, adB);
         }
       }
       for (int i = n0 + tid; i < n1; i += NT) a.x[i] = fma(alpha, a.d[i], a.x[i]);  // _osqp.py:664-668
@@ -474,11 +543,13 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
         B200QP_BARRIER_OR_DIE();
       }
     }
+    mark(5);
     k = kn;
   }
 
   if (cta == 0 && tid == 0) {
     KOut* o = a.out;
+    for (int i = 0; i < 8; ++i) o->phase_ns[i] = t_phase[i];
     o->status = status; o->iter = k; o->rho_updates = rho_updates;
     o->cg_iters = cg_total; o->barriers = (long long)sync.epoch;
     o->obj = obj; o->dual_obj = dobj; o->gap = gap; o->prim_res = prim_res; o->dual_res = dual_res;

@@ -458,19 +458,31 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
       const double tol = a.cg_tol_frac * r0max;
       for (int j = 0; j < a.cg_max_iter; ++j) {
         // C1 (local rows): w = rho .* (A_g p)
-        for (int base = m0; base < m1; base += NGM) {
-          const int row = base + grp_m;
-          const bool valid = row < m1;
-          const double acc = group_sum<LGM>(row_dot<LGM>(a.A, a.p, row, valid, lane_m));
-          if (valid && lane_m == 0) a.w[row] = a.rho_v[row] * acc;
+        for (int base = m0; base < m1; base += 2 * NGM) {
+          const int rowA = base + grp_m, rowB = rowA + NGM;
+          const bool okA = rowA < m1, okB = rowB < m1;
+          double accA, accB;
+          dot_pair<LGM>(a.A, a.p, rowA, okA, a.A, a.p, rowB, okB, lane_m, accA, accB);
+          accA = group_sum<LGM>(accA);
+          accB = group_sum<LGM>(accB);
+          if (lane_m == 0) {
+            if (okA) a.w[rowA] = a.rho_v[rowA] * accA;
+            if (okB) a.w[rowB] = a.rho_v[rowB] * accB;
+          }
         }
         B200QP_BARRIER_OR_DIE();
         // C2a: partial A_g' w over all n rows
-        for (int base = f0; base < f1; base += NGN) {
-          const int row = base + grp_n;
-          const bool valid = row < f1;
-          const double acc = group_sum<LGN>(row_dot<LGN>(a.At, a.w, row, valid, lane_n));
-          if (valid && lane_n == 0) my_part_w[row] = acc;
+        for (int base = f0; base < f1; base += 2 * NGN) {
+          const int rowA = base + grp_n, rowB = rowA + NGN;
+          const bool okA = rowA < f1, okB = rowB < f1;
+          double accA, accB;
+          dot_pair<LGN>(a.At, a.w, rowA, okA, a.At, a.w, rowB, okB, lane_n, accA, accB);
+          accA = group_sum<LGN>(accA);
+          accB = group_sum<LGN>(accB);
+          if (lane_n == 0) {
+            if (okA) my_part_w[rowA] = accA;
+            if (okB) my_part_w[rowB] = accB;
+          }
         }
         B200QP_XBAR_OR_DIE(0, nullptr, 0u);
         // C2b: my slice: Kp = sum_h partial_h + P p + sigma p ; <p, Kp> partial ; push Kp
@@ -535,11 +547,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
 #pragma unroll
       for (int i = 0; i < Z_K; ++i) v[i] = 0.0;
       v[Z_VU] = NEG_INF; v[Z_VL] = NEG_INF;
-      for (int base = m0; base < m1; base += NGM) {
-        const int row = base + grp_m;
-        const bool valid = row < m1;
-        const double ad = group_sum<LGM>(row_dot<LGM>(a.A, a.d, row, valid, lane_m));
-        if (valid && lane_m == 0) {
+      auto z_row = [&](int row, double ad) {
           const double ax_old = a.ax[row], z_old = a.z[row], y_old = a.y[row];
           const double rv = a.rho_v[row], ri = a.rho_inv[row], li = a.l[row], ui = a.u[row];
           const double zt = ax_old + ad;
@@ -572,6 +580,17 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
             if (lfin) v[Z_VL] = nanmax(v[Z_VL], -adx);
             v[Z_SUP] += (ufin ? ui * fmax(yn, 0.0) : 0.0) + (lfin ? li * fmin(yn, 0.0) : 0.0);
           }
+      };
+      for (int base = m0; base < m1; base += 2 * NGM) {
+        const int rowA = base + grp_m, rowB = rowA + NGM;
+        const bool okA = rowA < m1, okB = rowB < m1;
+        double adA, adB;
+        dot_pair<LGM>(a.A, a.d, rowA, okA, a.A, a.d, rowB, okB, lane_m, adA, adB);
+        adA = group_sum<LGM>(adA);
+        adB = group_sum<LGM>(adB);
+        if (lane_m == 0) {
+          if (okA) z_row(rowA, adA);
+          if (okB) z_row(rowB, adB);
         }
       }
       for (int i = u0 + tid; i < u1; i += NT) a.x[i] = fma(alpha, __ldcg(a.d + i), __ldcg(a.x + i));

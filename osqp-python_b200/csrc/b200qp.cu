@@ -751,6 +751,7 @@ static b200qp_int solve_end(b200qp_solver* solver) {
     std::snprintf(info->status, sizeof(info->status), "%s", status_string(o.status));
     w->stats.admm_iters = o.iter; w->stats.cg_iters = o.cg_iters; w->stats.grid_barriers = o.barriers;
     w->stats.kernel_ms = ms;
+    for (int i = 0; i < 8; ++i) w->stats.phase_ms[i] = o.phase_ns[i] * 1e-6;
     w->stats.algo_bytes = algo_bytes(w, o.iter, o.cg_iters, st->check_termination);
     if (w->dist.connected) { w->stats.grid = w->dist.G; }
     info->solve_time = now_s() - t0;

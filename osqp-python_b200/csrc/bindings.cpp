@@ -156,7 +156,9 @@ class Solver {
   py::dict stats() const {
     b200qp_stats st{};
     b200qp_get_stats(s_, &st);
-    return py::dict("admm_iters"_a = st.admm_iters, "cg_iters"_a = st.cg_iters, "grid_barriers"_a = st.grid_barriers,
+    py::list ph;
+    for (int i = 0; i < 8; ++i) ph.append(st.phase_ms[i]);
+    return py::dict("phase_ms"_a = ph, "admm_iters"_a = st.admm_iters, "cg_iters"_a = st.cg_iters, "grid_barriers"_a = st.grid_barriers,
                     "kernel_ms"_a = st.kernel_ms, "algo_bytes"_a = st.algo_bytes, "grid"_a = st.grid,
                     "block"_a = st.block, "n"_a = st.n, "m"_a = st.m, "nnzP_full"_a = st.nnzP_full, "nnzA"_a = st.nnzA);
   }

@@ -27,12 +27,12 @@ struct CsrMat {
 // Matrix streams are immutable while a kernel runs: read-only path, do not pollute L1.
 __device__ __forceinline__ double ld_stream(const double* p) {
   double v;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));   // not volatile: freely scheduled
   return v;
 }
 __device__ __forceinline__ int ld_stream(const int* p) {
   int v;
-  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 // Vectors change between phases of the persistent kernel and are written by other SMs:
