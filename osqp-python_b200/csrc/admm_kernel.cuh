@@ -76,6 +76,7 @@ __device__ __forceinline__ double row_dot(const CsrMat& M, const double* xv, int
     if (h0) x0 = ld_vec(xv + j0);
     if (h1) x1 = ld_vec(xv + j1);
     acc = fma(v1, x1, v0 * x0);
+#pragma unroll 4
     for (int k = k1 + LG; k < b; k += LG) acc = fma(ld_stream(M.val + k), ld_vec(xv + ld_stream(M.idx + k)), acc);
   }
   return acc;
@@ -103,7 +104,9 @@ __device__ __forceinline__ void dot_pair(const CsrMat& M1, const double* x1, int
   if (h21) y21 = ld_vec(x2 + j21);
   acc1 = fma(v11, y11, v10 * y10);
   acc2 = fma(v21, y21, v20 * y20);
+#pragma unroll 4
   for (int k = k11 + LG; k < b1; k += LG) acc1 = fma(ld_stream(M1.val + k), ld_vec(x1 + ld_stream(M1.idx + k)), acc1);
+#pragma unroll 4
   for (int k = k21 + LG; k < b2; k += LG) acc2 = fma(ld_stream(M2.val + k), ld_vec(x2 + ld_stream(M2.idx + k)), acc2);
 }
 template <int LG>

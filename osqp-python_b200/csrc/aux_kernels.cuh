@@ -67,12 +67,13 @@ __global__ void k_vec_fill(int len, double* __restrict__ out, double v) {
   if (i < len) out[i] = v;
 }
 
-// single-CTA reductions (setup only): out[0] = max|v.*s|, out[1] = sum v
-__global__ void k_absmax_sum(int len, const double* __restrict__ v, const double* __restrict__ s,
-                             double* __restrict__ out) {
+// two-stage reduction: out[0] = max|v.*s|, out[1] = sum v   (fixed order -> deterministic)
+constexpr int RED_BLOCKS = 256;
+__global__ void k_absmax_sum_partial(int len, const double* __restrict__ v, const double* __restrict__ s,
+                                     double* __restrict__ part /* [2*RED_BLOCKS] */) {
   __shared__ double sm[32], ss[32];
   double mx = 0.0, sum = 0.0;
-  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) {
     const double x = v[i];
     mx = nanmax(mx, fabs(x * (s ? s[i] : 1.0)));
     sum += x;
@@ -84,6 +85,13 @@ __global__ void k_absmax_sum(int len, const double* __restrict__ v, const double
   if (threadIdx.x == 0) {
     const int nw = blockDim.x >> 5;
     for (int w = 1; w < nw; ++w) { mx = nanmax(mx, sm[w]); sum += ss[w]; }
+    part[blockIdx.x] = mx; part[RED_BLOCKS + blockIdx.x] = sum;
+  }
+}
+__global__ void k_absmax_sum_final(int nblocks, const double* __restrict__ part, double* __restrict__ out) {
+  if (threadIdx.x == 0) {
+    double mx = part[0], sum = part[RED_BLOCKS];
+    for (int b = 1; b < nblocks; ++b) { mx = nanmax(mx, part[b]); sum += part[RED_BLOCKS + b]; }
     out[0] = mx; out[1] = sum;
   }
 }

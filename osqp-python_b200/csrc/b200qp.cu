@@ -126,7 +126,7 @@ struct Work {
   // staging / outputs
   DBuf<double> stage_d;          // max(n,m,nnz) doubles: H2D staging of caller arrays
   DBuf<int> stage_i;
-  DBuf<double> sol_n, sol_m, cert_n, cert_m, scal;
+  DBuf<double> sol_n, sol_m, cert_n, cert_m, scal, red_part;
   // polish workspace (allocated on first use)
   DBuf<double> pol_l, pol_u, pol_rho, pol_rhoinv, pol_Minv, bk_x, bk_z, bk_y, bk_ax;
   DBuf<int> pol_ctype, pol_count;
@@ -170,7 +170,7 @@ struct Work {
     mapA.free(); Pt_colptr.free(); Pt_rowidx.free(); posU.free(); posL.free();
     for (DBuf<double>* b : {&q, &pdiag, &D, &Dinv, &x, &d, &r, &p, &kp, &px, &Minv, &tmp_n, &tmp_n2, &l, &u, &E, &Einv,
                             &z, &y, &ax, &w2, &w, &rho_v, &rho_inv, &tmp_m, &stage_d, &sol_n, &sol_m, &cert_n, &cert_m,
-                            &scal, &red, &pol_l, &pol_u, &pol_rho, &pol_rhoinv, &pol_Minv, &bk_x, &bk_z, &bk_y, &bk_ax})
+                            &scal, &red, &red_part, &pol_l, &pol_u, &pol_rho, &pol_rhoinv, &pol_Minv, &bk_x, &bk_z, &bk_y, &bk_ax})
       b->free();
     pol_ctype.free(); pol_count.free();
     ctype.free(); stage_i.free(); part_n.free(); part_m.free(); ctrl.free(); out.free(); log.free();
@@ -216,6 +216,13 @@ void launch_scale(DevCsr& M, const double* rs, const double* cs, double scalar, 
     k_scale_csr<<<cdiv((long long)M.rows * 8, 256), 256, 0, s>>>(M.rows, M.ptr.p, M.idx.p, M.val.p, rs, cs, scalar);
 }
 
+// out[0] = max|v.*s|, out[1] = sum v  (two-stage, fixed order)
+void launch_absmax_sum(Work* w, int len, const double* v, const double* s, double* out) {
+  const int nb = std::max(1, std::min((int)RED_BLOCKS, cdiv(len, 1024)));
+  k_absmax_sum_partial<<<nb, 256, 0, w->stream>>>(len, v, s, w->red_part.p);
+  k_absmax_sum_final<<<1, 32, 0, w->stream>>>(nb, w->red_part.p, out);
+}
+
 void refresh_rho_and_precond(b200qp_solver* sv, bool retype) {
   Work* w = W(sv);
   const b200qp_settings* st = sv->settings;
@@ -231,11 +238,11 @@ void refresh_rho_and_precond(b200qp_solver* sv, bool retype) {
 void refresh_q_norms(b200qp_solver* sv) {
   Work* w = W(sv);
   double h[2];
-  k_absmax_sum<<<1, 1024, 0, w->stream>>>(w->n, w->q.p, nullptr, w->scal.p);
+  launch_absmax_sum(w, w->n, w->q.p, nullptr, w->scal.p);
   CK(cudaMemcpyAsync(h, w->scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
   CK(cudaStreamSynchronize(w->stream));
   w->nq_s = h[0];
-  k_absmax_sum<<<1, 1024, 0, w->stream>>>(w->n, w->q.p, w->Dinv.p, w->scal.p);
+  launch_absmax_sum(w, w->n, w->q.p, w->Dinv.p, w->scal.p);
   CK(cudaMemcpyAsync(h, w->scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
   CK(cudaStreamSynchronize(w->stream));
   w->nq_t = h[0];
@@ -584,6 +591,7 @@ b200qp_int b200qp_setup(b200qp_solver** solverp, const b200qp_csc* P, const b200
                             &w->tmp_m, &w->sol_m, &w->cert_m}) { b->alloc(m); b->zero(s); }
     w->ctype.alloc(m); w->ctype.zero(s);
     w->scal.alloc(8);
+    w->red_part.alloc(2 * RED_BLOCKS);
     const size_t stage_len = std::max<size_t>(std::max<size_t>(n + 2 * (size_t)m, (size_t)nnzA), (size_t)nnzPt) + 8;
     w->stage_d.alloc(stage_len);
     w->stage_i.alloc(std::max(nnzA, nnzPt) + 8);
@@ -614,10 +622,10 @@ b200qp_int b200qp_setup(b200qp_solver** solverp, const b200qp_csc* P, const b200
       double hq[2], hp[2] = {0, 0};
       if (w->P.nnz) {
         launch_row_absmax(w->P, w->tmp_n2.p, s);
-        k_absmax_sum<<<1, 1024, 0, s>>>(n, w->tmp_n2.p, nullptr, w->scal.p);
+        launch_absmax_sum(w, n, w->tmp_n2.p, nullptr, w->scal.p);
         CK(cudaMemcpyAsync(hp, w->scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
       }
-      k_absmax_sum<<<1, 1024, 0, s>>>(n, w->q.p, nullptr, w->scal.p + 2);
+      launch_absmax_sum(w, n, w->q.p, nullptr, w->scal.p + 2);
       CK(cudaMemcpyAsync(hq, w->scal.p + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
       auto lim = [](double v) { return v < MIN_SCALING ? 1.0 : (v > MAX_SCALING ? MAX_SCALING : v); };
@@ -1296,7 +1304,7 @@ b200qp_int b200qp_spmv_csr_host(b200qp_int rows, b200qp_int cols, const b200qp_i
 static double reduce_absmax(Work* w, int len, const double* v, double* sum_out = nullptr) {
   double h[2] = {0, 0};
   if (len) {
-    k_absmax_sum<<<1, 1024, 0, w->stream>>>(len, v, nullptr, w->scal.p + 4);
+    launch_absmax_sum(w, len, v, nullptr, w->scal.p + 4);
     CK(cudaMemcpyAsync(h, w->scal.p + 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
   }

@@ -292,3 +292,40 @@ def test_c4_full_size_properties():
     assert st["admm_iters"] == res.info.iter and st["nnzA"] == 10_000_000
     again = prob.solve()                      # warm-started from the solution: immediate
     assert again.info.status == "solved" and again.info.iter <= 25
+
+
+def test_c2_lasso_full_size_properties():
+    """BASELINE config 2 at full size: Lasso-as-QP n = 1e5, m = 2e5, data block 5e4 x 2.5e4 at 5 % density
+    (6.25e7 nnz, rows of 1250 and columns of 2500 entries).  Oracle cannot finish: KKT residuals instead."""
+    from b200qp import problems
+    P, q, A, l, u = problems.lasso_qp(25_000, 50_000, density=0.05, seed=1, box=True)
+    assert P.shape[0] == 100_000 and A.shape[0] == 200_000
+    res, rep, prob = _solve_and_check(P, q, A, l, u, eps=1e-3, max_iter=4000)
+    assert res.info.status in ("solved", "solved inaccurate")
+    scale = max(1.0, float(np.max(np.abs(q))))
+    assert rep["prim"] <= 5e-2 and rep["dual"] <= 5e-2 * scale
+    print("C2 full:", res.info.status, res.info.iter, prob.stats()["cg_iters"], prob.stats()["kernel_ms"], rep)
+
+
+def test_c3_svm_full_size_warm_start_polish():
+    """BASELINE config 3 at full size: SVM QP n = 5e4, m = 1e5 (n_feat 1e4, n_data 4e4, +2e4 box rows), adaptive rho,
+    then perturbed q + warm start + polish."""
+    import osqp
+    from b200qp import problems
+    P, q, A, l, u = problems.svm_qp(10_000, 40_000, density=0.01, seed=2, box_rows=20_000)
+    assert P.shape[0] == 50_000 and A.shape[0] == 100_000
+    prob = osqp.OSQP()
+    prob.setup(P, q, A, l, u, verbose=False, adaptive_rho=True, polishing=True, max_iter=10000)
+    r1 = prob.solve()
+    assert r1.info.status == "solved"
+    rep = problems.kkt_report(P, q, A, l, u, r1.x, r1.y)
+    assert rep["prim"] <= 1e-2 and rep["dual"] <= 1e-2
+    q2 = q * (1 + 0.01 * np.cos(np.arange(len(q))))
+    prob.update(q=q2)
+    prob.warm_start(x=r1.x, y=r1.y)
+    r2 = prob.solve()
+    assert r2.info.status == "solved" and r2.info.iter <= r1.info.iter
+    assert r2.info.status_polish in (1, -1)
+    rep2 = problems.kkt_report(P, q2, A, l, u, r2.x, r2.y)
+    assert rep2["prim"] <= 1e-2 and rep2["dual"] <= 1e-2
+    print("C3 full:", r1.info.iter, r2.info.iter, r1.info.status_polish, r2.info.status_polish, rep, rep2)
