@@ -157,12 +157,14 @@ def bench(args, rank, world, local, B):
     iters = cg = 0
     bytes_algo = 0.0
     res = None
+    phases = [0.0] * 8
     for i in range(args.steps):
         t0 = time.perf_counter()
         res = step(i)
         wall_ms += 1e3 * (time.perf_counter() - t0)
         st = solver.stats()
         dev_ms += st["kernel_ms"]; iters += st["admm_iters"]; cg += st["cg_iters"]; bytes_algo += st["algo_bytes"]
+        phases = [a + b for a, b in zip(phases, st["phase_ms"])]
     dist.barrier(); torch.cuda.synchronize()
     clocks = sampler.stop()
     # max over ranks of the device time and of the wall time
@@ -180,6 +182,8 @@ def bench(args, rank, world, local, B):
                        "pcg_iters_per_admm_iter": cg / max(iters, 1), "status": res.info.status,
                        "partition": f"{world} row slabs of A (balanced by nnz), n-vectors replicated; partial A_g'w "
                                     "reduced over NVLink inside the persistent kernel (fused reduce-scatter + all-gather)",
+                       "phase_ms_per_step_rank0": dict(zip(["R", "C1_Ap", "C2b_reduce_Kp_push", "C3_axpy_dots", "C4_p", "Z",
+                                                            "C2a_partial_AtW", "x7"], [round(v / args.steps, 3) for v in phases])),
                        "l2": "inputs larger than L2; no flush between steps", "grid": f"{st['grid']}x{st['block']} per GPU",
                        "setup_s": t_setup, "settings": dict(B.SOLVE_KW)},
             "roofline": {"bound": "hbm", "kernel": "b200qp::admm_kernel_dist (persistent, one launch per rank per solve)",

@@ -221,23 +221,28 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
   // coalesced reduce-scatter pre-pass for this CTA's rows of the slice: sum over ranks, rank order
   auto gather_partials = [&](bool second) {
     for (int i = s0 + tid; i < s1; i += NT) {
-      double acc = ld_peer(x.part_w[0] + i);
-      for (int h = 1; h < world; ++h) acc += ld_peer(x.part_w[h] + i);
-      x.sum_w[i] = acc;
-      if (second) {
-        double acy = ld_peer(x.part_y[0] + i);
-        for (int h = 1; h < world; ++h) acy += ld_peer(x.part_y[h] + i);
-        x.sum_y[i] = acy;
+      // all peer loads first (NVLink round trips overlap), then the sum in rank order
+      double vw[MAXW], vy[MAXW];
+#pragma unroll
+      for (int h = 0; h < MAXW; ++h) {
+        vw[h] = (h < world) ? ld_peer(x.part_w[h] + i) : 0.0;
+        vy[h] = (second && h < world) ? ld_peer(x.part_y[h] + i) : 0.0;
       }
+      double acc = vw[0], acy = vy[0];
+#pragma unroll
+      for (int h = 1; h < MAXW; ++h) if (h < world) { acc += vw[h]; acy += vy[h]; }
+      x.sum_w[i] = acc;
+      if (second) x.sum_y[i] = acy;
     }
     __syncthreads();
   };
   // push this CTA's finished rows of a replicated vector to every other rank (all-gather by stores)
   auto push_rows = [&](double* const* table, const double* local) {
-    for (int h = 0; h < world; ++h) {
-      if (h == rank) continue;
-      double* dst = table[h];
-      for (int i = s0 + tid; i < s1; i += NT) st_sys_f64(dst + i, __ldcg(local + i));
+    for (int i = s0 + tid; i < s1; i += NT) {
+      const double v = __ldcg(local + i);
+#pragma unroll
+      for (int h = 0; h < MAXW; ++h)
+        if (h < world && h != rank) st_sys_f64(table[h] + i, v);
     }
   };
 
@@ -252,6 +257,13 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
     }
   }
   B200QP_BARRIER_OR_DIE();
+
+  __shared__ long long t_phase[8];
+  __shared__ unsigned long long t_mark;
+  if (tid == 0) { for (int i = 0; i < 8; ++i) t_phase[i] = 0; t_mark = global_timer_ns(); }
+  auto mark = [&](int id) {
+    if (cta == 0 && tid == 0) { const unsigned long long now = global_timer_ns(); t_phase[id] += (long long)(now - t_mark); t_mark = now; }
+  };
 
   // ---- R phase, distributed: partial A_g' w2 (and A_g' y) -> reduce over ranks -> r, p everywhere
   auto phase_R = [&](bool full, bool lite) -> bool {
@@ -413,6 +425,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
     const bool full = chk || adp;
 
     if (!phase_R(full, false)) B200QP_DIE();
+    mark(0);
     if (full && a.verbose && cta == 0 && tid == 0 && chk && rank == 0) {
       const int row = (k / (a.check_term > 0 ? a.check_term : 1)) - 1;
       if (row >= 0 && row < a.log_cap) {
@@ -471,6 +484,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
           }
         }
         B200QP_BARRIER_OR_DIE();
+        mark(1);
         // C2a: partial A_g' w over all n rows
         for (int base = f0; base < f1; base += 2 * NGN) {
           const int rowA = base + grp_n, rowB = rowA + NGN;
@@ -485,6 +499,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
           }
         }
         B200QP_XBAR_OR_DIE(0, nullptr, 0u);
+        mark(6);
         // C2b: my slice: Kp = sum_h partial_h + P p + sigma p ; <p, Kp> partial ; push Kp
         gather_partials(false);
         double v1[1] = {0.0};
@@ -504,6 +519,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
         double* bk = bank();
         block_reduce_store<1>(v1, 0u, bk, G, s_red);
         B200QP_XBAR_OR_DIE(1, bk, 0u);
+        mark(2);
         const double pkp = s_tot[0];
         if (!(pkp > 0.0)) { status = 9; break; }
         const double aj = rz / pkp;
@@ -523,12 +539,14 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
         block_reduce_store<2>(v2, 2u, bk, G, s_red);
         B200QP_BARRIER_OR_DIE();
         grid_reduce_load<2>(bk, G, 2u, s_tot);
+        mark(3);
         const double rz_new = s_tot[0], rmax = s_tot[1];
         if (!(rmax > tol) || j + 1 == a.cg_max_iter) break;
         const double bj = rz_new / rz;
         rz = rz_new;
         for (int i = u0 + tid; i < u1; i += NT) a.p[i] = fma(bj, __ldcg(a.p + i), __ldcg(a.Minv + i) * __ldcg(a.r + i));
         B200QP_BARRIER_OR_DIE();
+        mark(4);
       }
       if (status) break;
     }
@@ -606,11 +624,13 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
         B200QP_BARRIER_OR_DIE();
       }
     }
+    mark(5);
     k = kn;
   }
 
   if (cta == 0 && tid == 0) {
     KOut* o = a.out;
+    for (int i = 0; i < 8; ++i) o->phase_ns[i] = t_phase[i];
     o->status = status; o->iter = k; o->rho_updates = rho_updates;
     o->cg_iters = cg_total; o->barriers = (long long)sync.epoch;
     o->xepoch = (long long)xs.xepoch;
