@@ -21,6 +21,7 @@
 #include "admm_kernel_dist.cuh"
 #include "aux_kernels.cuh"
 #include "spmv_kernels.cuh"
+#include "tiling.h"
 
 using namespace b200qp;
 
@@ -270,7 +271,8 @@ void make_partition(int rows, int G, const std::vector<const std::vector<int>*>&
   part[G] = rows;
 }
 
-int pick_lg(double avg) { return avg <= 6.0 ? 4 : (avg <= 24.0 ? 8 : 32); }
+// lanes per row of the in-kernel SpMV (tools/gather_bench.cu: 4 lanes beat 8 at 10 nnz/row, 63 vs 76 us)
+int pick_lg(double avg) { return avg <= 12.0 ? 4 : (avg <= 48.0 ? 8 : 32); }
 
 typedef void (*admm_fn)(const KArgs);
 admm_fn pick_kernel(int lgn, int lgm) {
@@ -647,8 +649,10 @@ b200qp_int b200qp_setup(b200qp_solver** solverp, const b200qp_csc* P, const b200
     // ---- launch geometry + static partitions
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, w->device));
-    w->lgn = pick_lg(n ? (double)(w->P.nnz + w->At.nnz) / n : 1.0);
+    w->lgn = pick_lg(n ? (double)(w->P.nnz + w->At.nnz) / n / 2 : 1.0);   // P and A' rows are walked side by side
     w->lgm = pick_lg(m ? (double)w->A.nnz / m : 1.0);
+    if (const char* e = std::getenv("B200QP_LGN")) { const int v = std::atoi(e); if (v == 4 || v == 8 || v == 32) w->lgn = v; }
+    if (const char* e = std::getenv("B200QP_LGM")) { const int v = std::atoi(e); if (v == 4 || v == 8 || v == 32) w->lgm = v; }
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)pick_kernel(w->lgn, w->lgm), NT, 0));
     if (occ < 1) throw (int)B200QP_ALGEBRA_LOAD_ERROR;
@@ -1162,8 +1166,9 @@ b200qp_int b200qp_dist_solve_group(b200qp_solver** group, b200qp_int world) {
 struct b200qp_spmv_plan {
   int device = 0;
   DevCsr M;
-  DBuf<int> tiles;
-  int T = 0;
+  DBuf<int4> tiles;
+  DBuf<int> cta_tile;
+  int T = 0, grid_tile = 1;
   DBuf<double> x, y;
   DBuf<char> flush;
   cudaStream_t stream = nullptr;
@@ -1174,19 +1179,6 @@ struct b200qp_spmv_plan {
 b200qp_int b200qp_spmv_num_variants(void) { return 3; }
 const char* b200qp_spmv_variant_name(b200qp_int v) {
   return v == 0 ? "group" : v == 1 ? "stream-tma" : v == 2 ? "scalar" : "?";
-}
-
-static void make_tiles(const std::vector<int>& ptr, int rows, std::vector<int>& tiles) {
-  tiles.clear();
-  int r = 0;
-  while (r < rows) {
-    tiles.push_back(r);
-    int e = r + 1;   // at least one row (a single long row becomes its own tile)
-    while (e < rows && e - r < ST_NT && ptr[e + 1] - ptr[r] <= ST_TILE) ++e;
-    if (ptr[e] - ptr[r] > ST_TILE) e = r + 1;
-    r = e;
-  }
-  tiles.push_back(rows);
 }
 
 b200qp_int b200qp_spmv_plan_create(b200qp_spmv_plan** planp, b200qp_int rows, b200qp_int cols, const b200qp_int* ptr,
@@ -1204,16 +1196,23 @@ b200qp_int b200qp_spmv_plan_create(b200qp_spmv_plan** planp, b200qp_int rows, b2
     std::vector<int> p(ptr, ptr + rows + 1), i(idx, idx + nnz);
     std::vector<double> v(val, val + nnz);
     pl->M.upload(rows, cols, p, i, v, pl->stream);
-    std::vector<int> tiles;
-    make_tiles(p, rows, tiles);
-    pl->T = (int)tiles.size() - 1;
-    pl->tiles.alloc(tiles.size());
-    pl->tiles.upload(tiles.data(), tiles.size(), pl->stream);
     pl->x.alloc(cols); pl->y.alloc(rows);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     pl->sms = prop.multiProcessorCount;
-    CK(cudaFuncSetAttribute(k_spmv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+    CK(cudaFuncSetAttribute(k_spmv_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_tile, NT, TS_SMEM));
+    std::vector<int4> tiles;
+    std::vector<int> cta_tile, part;
+    make_tiles(rows, p.data(), TS_TILE, TS_MAXROWS, tiles);
+    pl->T = (int)tiles.size();
+    pl->grid_tile = std::max(1, std::min(pl->T, pl->sms * std::max(occ, 1)));
+    partition_tiles(tiles, rows, pl->grid_tile, cta_tile, part);
+    pl->tiles.alloc(tiles.size());
+    pl->tiles.upload(tiles.data(), tiles.size(), pl->stream);
+    pl->cta_tile.alloc(cta_tile.size());
+    pl->cta_tile.upload(cta_tile.data(), cta_tile.size(), pl->stream);
     CK(cudaStreamSynchronize(pl->stream));
   } catch (int code) {
     delete pl;
@@ -1228,10 +1227,8 @@ static void spmv_launch(b200qp_spmv_plan* pl, int variant) {
   const int rows = M.rows;
   if (!rows) return;
   if (variant == 1) {
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_stream, ST_NT, ST_SMEM);
-    const int grid = std::max(1, std::min(pl->T, pl->sms * std::max(occ, 1)));
-    k_spmv_stream<<<grid, ST_NT, ST_SMEM, pl->stream>>>(M, pl->tiles.p, pl->T, pl->x.p, pl->y.p);
+    const TileMat TM{M.rows, M.cols, M.nnz, pl->T, M.ptr, M.idx, M.val, pl->tiles.p, nullptr};
+    k_spmv_tile<<<pl->grid_tile, NT, TS_SMEM, pl->stream>>>(TM, pl->cta_tile.p, pl->x.p, pl->y.p);
   } else if (variant == 2) {
     k_spmv_scalar<<<cdiv(rows, 256), 256, 0, pl->stream>>>(M, pl->x.p, pl->y.p);
   } else {
@@ -1239,6 +1236,7 @@ static void spmv_launch(b200qp_spmv_plan* pl, int variant) {
     const int grid = cdiv((long long)rows * lg, 256);
     if (lg == 4) k_spmv_group<4><<<grid, 256, 0, pl->stream>>>(M, pl->x.p, pl->y.p);
     else if (lg == 8) k_spmv_group<8><<<grid, 256, 0, pl->stream>>>(M, pl->x.p, pl->y.p);
+    else if (lg == 2) k_spmv_group<2><<<grid, 256, 0, pl->stream>>>(M, pl->x.p, pl->y.p);
     else k_spmv_group<32><<<grid, 256, 0, pl->stream>>>(M, pl->x.p, pl->y.p);
   }
 }
@@ -1276,7 +1274,7 @@ b200qp_int b200qp_spmv_plan_run(b200qp_spmv_plan* pl, const b200qp_float* x_host
 void b200qp_spmv_plan_destroy(b200qp_spmv_plan* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
-  pl->M.free(); pl->tiles.free(); pl->x.free(); pl->y.free(); pl->flush.free();
+  pl->M.free(); pl->tiles.free(); pl->cta_tile.free(); pl->x.free(); pl->y.free(); pl->flush.free();
   if (pl->e0) cudaEventDestroy(pl->e0);
   if (pl->e1) cudaEventDestroy(pl->e1);
   if (pl->stream) cudaStreamDestroy(pl->stream);
