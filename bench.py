@@ -15,6 +15,8 @@ One *step* = one complete cold-start solve() of that QP to the default tolerance
   roofline     the dominant (only hot) kernel is the persistent ADMM kernel: algorithmic HBM bytes of
                the launch (byte model in DESIGN.md, computed by the engine from its own iteration
                counters) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+  batch        BASELINE configs[4] as a sub-object: 8192 independent MPC QPs sharded over the GPUs (QPs/s,
+               device-timed and end to end; b200qp/batchbench.py).
   cpu_baseline the CPU oracle (port of the reference algorithm, engine-spec PCG mode because a direct
                factorisation cannot finish at this size -- SURVEY.md 8d) on a bounded sample.
   --impl reference   times that CPU implementation as its own arm (rank 0 only).
@@ -260,6 +262,10 @@ def run_ours(args):
     }
     if not args.no_spmv:
         line["spmv"] = spmv_line(A, peak)
+    if not args.no_batch:
+        from b200qp import batchbench
+        line["batch"] = batchbench.batch_line(args, with_cpu=not args.no_cpu_baseline)
+        line["gpu_launches"] += args.steps * line["batch"]["gpu_launches_per_step"]
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(P, q, A, l, u)
     else:
@@ -275,6 +281,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spmv", action="store_true")
+    ap.add_argument("--no-batch", action="store_true", help="skip the config-5 (batched MPC QPs) line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -217,6 +217,41 @@ b200qp_int b200qp_dist_connect_ipc(b200qp_solver *solver, const void *handles_wo
 b200qp_int b200qp_dist_connect_local(b200qp_solver **group, b200qp_int world);
 b200qp_int b200qp_dist_solve_group(b200qp_solver **group, b200qp_int world);
 
+/* ---- batched independent QPs (BASELINE.json configs[4]; SURVEY.md 8e "replicas only") ------------------
+ * `batch` QPs that share one (P, A) and differ in q, l, u; one CTA per QP, every vector of a QP in shared
+ * memory.  Replaces the reference's batched caller, which loops solver objects over a thread pool and
+ * re-uses one setup through update() (src/osqp/nn/torch.py:128-164, 200-217): element b is the QP a
+ * reference user gets from setup(P, q[0], A, l[0], u[0]) followed by update(q=q[b], l=l[b], u=u[b]) and
+ * solve() -- same scaling (D, E, c of element 0; update() never re-equilibrates, _osqp.py:1312-1367), own
+ * ADMM state and own rho.  q is batch x n, l and u are batch x m, row-major, HOST buffers consumed before
+ * the call returns.  Multi-GPU: one b200qp_batch per GPU (settings->device) over a shard of the batch; no
+ * collective.  Polish is not run on batch elements (status_polish stays 0). */
+typedef struct b200qp_batch b200qp_batch;
+typedef struct {            /* per element; mirrors the OSQPInfo fields that are per solve */
+  b200qp_int status_val, iter, rho_updates, cg_iter;
+  b200qp_float obj_val, dual_obj_val, prim_res, dual_res, rho, rho_estimate;
+} b200qp_batch_info;
+typedef struct {
+  long long admm_iters, cg_iters;   /* summed over the batch, last solve */
+  double kernel_ms;                 /* device time of the batch kernel, CUDA events on its stream */
+  double setup_time, update_time, solve_time; /* host wall clock, seconds */
+  b200qp_int grid, block, smem_bytes, batch, n, m;
+} b200qp_batch_stats;
+b200qp_int b200qp_batch_setup(b200qp_batch **batchp, b200qp_int batch, const b200qp_csc *P, const b200qp_float *q,
+                              const b200qp_csc *A, const b200qp_float *l, const b200qp_float *u, b200qp_int m,
+                              b200qp_int n, const b200qp_settings *settings);
+b200qp_int b200qp_batch_solve(b200qp_batch *b);
+b200qp_int b200qp_batch_update_data_vec(b200qp_batch *b, const b200qp_float *q_new, const b200qp_float *l_new,
+                                        const b200qp_float *u_new);
+b200qp_int b200qp_batch_warm_start(b200qp_batch *b, const b200qp_float *x, const b200qp_float *y);
+b200qp_int b200qp_batch_update_settings(b200qp_batch *b, const b200qp_settings *new_settings);
+b200qp_int b200qp_batch_update_rho(b200qp_batch *b, b200qp_float rho_new);
+b200qp_int b200qp_batch_get_solution(const b200qp_batch *b, b200qp_float *x, b200qp_float *y,
+                                     b200qp_float *prim_inf_cert, b200qp_float *dual_inf_cert);
+b200qp_int b200qp_batch_get_info(const b200qp_batch *b, b200qp_batch_info *info);
+b200qp_int b200qp_batch_get_stats(const b200qp_batch *b, b200qp_batch_stats *stats);
+b200qp_int b200qp_batch_cleanup(b200qp_batch *b);
+
 /* ---- hot operator, standalone (parity tests and the SpMV roofline line of bench.py) --------
  * y = M x for a CSR matrix (fp64 values, int32 indices).  *_host: host buffers in and out.
  * The device-handle form keeps the matrix and vectors resident and times `reps` launches with

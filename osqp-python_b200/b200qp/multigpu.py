@@ -171,6 +171,10 @@ def bench(args, rank, world, local, B):
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=torch.device("cuda", local))
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, wall_ms = float(t[0]), float(t[1])
+    batch = None
+    if not getattr(args, "no_batch", False):
+        from b200qp import batchbench
+        batch = batchbench.batch_line(args, rank, world, local, dist=dist, torch=torch, with_cpu=False)
     if rank == 0:
         peak, peak_src = B.measured_peak()
         achieved = bytes_algo / (dev_ms * 1e-3) / 1e9      # whole-job algorithmic bytes (same model as N = 1)
@@ -197,6 +201,9 @@ def bench(args, rank, world, local, B):
             "clocks": clocks,
             "cpu_baseline": {"value": None, "unit": B.UNIT, "cores": 0, "kind": "port", "sample": "N = 1 run only"},
         }
+        if batch is not None:
+            line["batch"] = batch
+            line["gpu_launches"] += args.steps * batch["gpu_launches_per_step"] * world
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -152,6 +152,23 @@ def mpc_qp(seed=4, horizon=10, nx=8, nu=4, shared_seed=4):
     return P, q, A, np.concatenate(l), np.concatenate(u)
 
 
+def mpc_batch(batch, seed0=4, horizon=10, nx=8, nu=4, shared_seed=4):
+    """Config 5: `batch` MPC QPs (seeds seed0 .. seed0+batch-1) that share P, q, A and differ in the initial
+    state, i.e. in the first nx entries of l and u.  Returns (P, q, A, l, u) with l, u of shape (batch, m);
+    element b equals mpc_qp(seed=seed0 + b)."""
+    P, q, A, l0, u0 = mpc_qp(seed=seed0, horizon=horizon, nx=nx, nu=nu, shared_seed=shared_seed)
+    rs = np.random.default_rng(shared_seed)
+    Adyn = rs.standard_normal((nx, nx))
+    Adyn = 0.9 * Adyn / max(abs(np.linalg.eigvals(Adyn)))
+    l = np.tile(l0, (batch, 1))
+    u = np.tile(u0, (batch, 1))
+    for b in range(batch):
+        beq = Adyn @ np.random.default_rng(seed0 + b).standard_normal(nx)
+        l[b, :nx] = beq
+        u[b, :nx] = beq
+    return P, q, A, l, u
+
+
 def kkt_report(P, q, A, l, u, x, y):
     """Size-independent optimality check of a returned (x, y): residuals of the unscaled KKT system."""
     Pf = sparse.csc_matrix(P)

@@ -44,6 +44,20 @@ def _stamp(target, sources):
         f.write(_digest(sources))
 
 
+def _deps(unit):
+    """The unit plus every local header it (transitively) includes."""
+    import re
+    seen, todo = [], [unit]
+    while todo:
+        f = os.path.normpath(todo.pop())
+        if f in seen or not os.path.exists(f):
+            continue
+        seen.append(f)
+        for inc in re.findall(r'#include\s+"([^"]+)"', open(f).read()):
+            todo.append(os.path.join(os.path.dirname(f), inc))
+    return seen
+
+
 def _run(cmd):
     print("+", " ".join(cmd), flush=True)
     subprocess.check_call(cmd)
@@ -51,13 +65,28 @@ def _run(cmd):
 
 def build(force=False, verbose_ptxas=False):
     os.makedirs(LIBDIR, exist_ok=True)
-    cu_sources = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    cu_sources = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
     cu_sources.append(os.path.join(ROOT, "include", "b200qp.h"))
-    if force or _stale(LIB, cu_sources):
-        flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-        if verbose_ptxas:
-            flags += ["-Xptxas", "-v"]
-        _run([NVCC] + flags + ["-o", LIB, os.path.join(CSRC, "b200qp.cu")])
+    units = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+    objs = [os.path.join(LIBDIR, os.path.basename(u)[:-3] + ".o") for u in units]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math") and f != "-shared"]
+    if verbose_ptxas:
+        flags += ["-Xptxas", "-v"]
+    # one object per translation unit (rebuilt when the unit or a header it includes changed), compiled
+    # side by side, then one link
+    procs = []
+    for u, o in zip(units, objs):
+        deps = _deps(u)
+        if force or verbose_ptxas or _stale(o, deps):
+            cmd = [NVCC] + flags + ["-c", "-o", o, u]
+            print("+", " ".join(cmd), flush=True)
+            procs.append((cmd, subprocess.Popen(cmd), o, deps))
+    for cmd, pr, o, deps in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+        _stamp(o, deps)
+    if procs or force or _stale(LIB, cu_sources):
+        _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs)
         _stamp(LIB, cu_sources)
     bind_src = os.path.join(CSRC, "bindings.cpp")
     ext_sources = [bind_src, os.path.join(ROOT, "include", "b200qp.h")]

@@ -1,0 +1,515 @@
+// admm_batch.cuh -- batched ADMM kernel: many independent QPs that share one (P, A), one CTA per QP.
+//
+// BASELINE.json configs[4] (8192 MPC QPs, n = 120, m = 240); SURVEY.md 8e "config 5: replicas only, no
+// collective".  The reference solves such a batch by looping solver objects over a thread pool
+// (src/osqp/nn/torch.py:128-164, 200-217), re-using one setup through update(q, l, u)
+// (src/osqp/nn/torch.py:136-140).  Element b of the batch is exactly that QP: the shared scaled matrices of
+// one setup(), its own q, l, u, its own ADMM state (x, z, y, rho).
+//
+// Same iteration as admm_kernel.cuh (reference loop src/osqppurepy/_osqp.py:1188-1306): residual-correction
+// Jacobi-PCG on K = P + sigma I + A' rho A, relaxation, box projection, dual update, residuals, infeasibility
+// certificates, adaptive rho.  What changes is where things live:
+//   * every vector of the QP (8 n-vectors + 8 m-vectors) is in SHARED MEMORY for the whole solve; global
+//     memory is touched once to load q, l, u (and the warm start) and once to store x, y and the info block;
+//   * the shared matrices are read through L1 (__ldg): all CTAs of an SM walk the same 30 KB;
+//   * phases are separated by __syncthreads, reductions are CTA-level and fixed-order (deterministic);
+//   * CTAs pull QP indices from a global counter, so QPs that need 25 and 200 iterations balance out.
+#pragma once
+#include "device_common.cuh"
+
+namespace b200qp {
+
+constexpr int NTB = 256;        // threads per CTA of the batch kernel
+constexpr int NWB = NTB / 32;
+
+struct BInfo {                  // per QP, written at exit (64 bytes)
+  int status, iter, rho_updates, cg_iters;
+  double obj, dual_obj, prim_res, dual_res, rho, rho_estimate;
+};
+
+struct BArgs {
+  int n, m, batch;
+  CsrMat P, A, At;                                   // shared, scaled (c D P D, E A D, D A' E)
+  const double *pdiag, *D, *Dinv, *E, *Einv;         // shared
+  const double *q, *l, *u;                           // [batch][n | m], scaled
+  double *xs, *zs, *ys, *rho_b;                      // per-QP ADMM state, scaled space (kept between solves)
+  double *sol_x, *sol_y, *cert_n, *cert_m;           // [batch][n | m], unscaled results
+  BInfo* info;
+  int* next;                                         // work counter
+  double sigma, alpha, eps_abs, eps_rel, eps_pinf, eps_dinf, c, adapt_tol, cg_tol_frac, rho_eq_factor, time_limit_ns;
+  int max_iter, check_term, adaptive_rho, adapt_interval, cg_max_iter, cg_precond, unscale, rho_is_vec, check_dualgap;
+  int warm;                                          // 1: start from (xs, ys), z = A x; 0: cold start
+};
+
+// CTA reduction of K slots (sum or NaN-propagating max per maxmask bit); result in s_tot[0..K)
+template <int K>
+__device__ __forceinline__ void cta_reduce(double (&v)[K], unsigned maxmask, double* s_red, double* s_tot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double r = warp_combine(v[k], (maxmask >> k) & 1u);
+    if (lane == 0) s_red[k * NWB + warp] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    const bool mx = (maxmask >> threadIdx.x) & 1u;
+    double acc = s_red[threadIdx.x * NWB];
+#pragma unroll
+    for (int w = 1; w < NWB; ++w) acc = combine(acc, s_red[threadIdx.x * NWB + w], mx);
+    s_tot[threadIdx.x] = acc;
+  }
+  __syncthreads();
+}
+
+// dot of one shared-matrix row (through L1) with a shared-memory vector
+template <int LG>
+__device__ __forceinline__ double brow_dot(const CsrMat& M, const double* xs, int row, bool valid, int lane) {
+  double acc = 0.0;
+  if (valid) {
+    const int a = __ldg(M.ptr + row), b = __ldg(M.ptr + row + 1);
+    for (int k = a + lane; k < b; k += LG) acc = fma(__ldg(M.val + k), xs[__ldg(M.idx + k)], acc);
+  }
+  return acc;
+}
+template <int LG>
+__device__ __forceinline__ void brow_dot2(const CsrMat& M, const double* x1, const double* x2, int row, bool valid,
+                                          int lane, double& a1, double& a2) {
+  a1 = 0.0; a2 = 0.0;
+  if (valid) {
+    const int a = __ldg(M.ptr + row), b = __ldg(M.ptr + row + 1);
+    for (int k = a + lane; k < b; k += LG) {
+      const double v = __ldg(M.val + k);
+      const int j = __ldg(M.idx + k);
+      a1 = fma(v, x1[j], a1);
+      a2 = fma(v, x2[j], a2);
+    }
+  }
+}
+template <int LG>
+__device__ __forceinline__ double brow_dot_sq(const CsrMat& M, const double* xs, int row, bool valid, int lane) {
+  double acc = 0.0;
+  if (valid) {
+    const int a = __ldg(M.ptr + row), b = __ldg(M.ptr + row + 1);
+    for (int k = a + lane; k < b; k += LG) { const double v = __ldg(M.val + k); acc = fma(v * v, xs[__ldg(M.idx + k)], acc); }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ int btype_of(double li, double ui) {   // reference: _osqp.py:499-524
+  return (ui - li < RHO_TOL) ? 1 : ((li < -INF_THRESH && ui > INF_THRESH) ? -1 : 0);
+}
+__device__ __forceinline__ double brho_of(int ct, double rho, int rho_is_vec, double eq_factor) {
+  if (!rho_is_vec) return rho;
+  return ct == 1 ? eq_factor * rho : (ct == -1 ? RHO_MIN : rho);
+}
+
+// reduction slots (same meaning as in admm_kernel.cuh)
+enum { BR_RZ = 0, BR_R0, BR_SDUAL, BR_SATY, BR_SPX, BR_TDUAL, BR_TATY, BR_TPX, BR_XPX, BR_QX, BR_NDX, BR_QDX, BR_TL, BR_K };
+constexpr unsigned BR_MAXMASK = (1u << BR_R0) | (1u << BR_SDUAL) | (1u << BR_SATY) | (1u << BR_SPX) | (1u << BR_TDUAL) |
+                                (1u << BR_TATY) | (1u << BR_TPX) | (1u << BR_NDX) | (1u << BR_TL);
+enum { BZ_SPRIM = 0, BZ_SAX, BZ_SZ, BZ_TPRIM, BZ_TAX, BZ_TZ, BZ_NDY, BZ_LHS, BZ_VU, BZ_VL, BZ_SUP, BZ_K };
+constexpr unsigned BZ_MAXMASK = (1u << BZ_SPRIM) | (1u << BZ_SAX) | (1u << BZ_SZ) | (1u << BZ_TPRIM) | (1u << BZ_TAX) |
+                                (1u << BZ_TZ) | (1u << BZ_NDY) | (1u << BZ_VU) | (1u << BZ_VL);
+
+inline size_t batch_smem_bytes(int n, int m) {
+  return ((size_t)8 * n + (size_t)8 * m + KMAX * NWB + KMAX) * sizeof(double);
+}
+
+template <int LGN, int LGM>
+__global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constant__ BArgs a) {
+  extern __shared__ double sm[];
+  __shared__ int s_qp;
+  const int n = a.n, m = a.m, tid = threadIdx.x;
+  double* const q = sm;
+  double* const x = q + n;
+  double* const d = x + n;
+  double* const r = d + n;
+  double* const p = r + n;
+  double* const kp = p + n;
+  double* const px = kp + n;
+  double* const Minv = px + n;
+  double* const l = Minv + n;
+  double* const u = l + m;
+  double* const z = u + m;
+  double* const y = z + m;
+  double* const ax = y + m;
+  double* const w2 = ax + m;
+  double* const w = w2 + m;
+  double* const rho_v = w + m;
+  double* const s_red = rho_v + m;
+  double* const s_tot = s_red + KMAX * NWB;
+
+  constexpr int NGN = NTB / LGN, NGM = NTB / LGM;
+  const int lane_n = tid & (LGN - 1), grp_n = tid / LGN;
+  const int lane_m = tid & (LGM - 1), grp_m = tid / LGM;
+  const double NEG_INF = __longlong_as_double(0xfff0000000000000LL);
+  const double NANV = __longlong_as_double(0x7ff8000000000000LL);
+  const double alpha = a.alpha, sigma = a.sigma;
+  const double cinv = 1.0 / a.c;
+  const double c_eff = a.unscale ? a.c : 1.0, cinv_eff = a.unscale ? cinv : 1.0;
+  const double* Dinv_t = a.unscale ? a.Dinv : nullptr;
+  const double* D_t = a.unscale ? a.D : nullptr;
+  const double* Einv_t = a.unscale ? a.Einv : nullptr;
+  const double* E_t = a.unscale ? a.E : nullptr;
+
+  for (;;) {
+    __syncthreads();                       // the previous QP is completely stored
+    if (tid == 0) s_qp = atomicAdd(a.next, 1);
+    __syncthreads();
+    const int qp = s_qp;
+    if (qp >= a.batch) break;
+    const unsigned long long t_start = global_timer_ns();
+    const size_t on = (size_t)qp * n, om = (size_t)qp * m;
+
+    // ---------------------------------------------------------------- load the QP
+    double rho = a.rho_b[qp];
+    double nq_s = 0.0, nq_t = 0.0;
+    {
+      double v[2] = {0.0, 0.0};
+      for (int i = tid; i < n; i += NTB) {
+        const double qi = a.q[on + i];
+        q[i] = qi;
+        x[i] = a.warm ? a.xs[on + i] : 0.0;
+        d[i] = 0.0;
+        v[0] = nanmax(v[0], fabs(qi));
+        v[1] = nanmax(v[1], fabs((Dinv_t ? __ldg(Dinv_t + i) : 1.0) * qi));
+      }
+      for (int i = tid; i < m; i += NTB) {
+        const double li = a.l[om + i], ui = a.u[om + i];
+        l[i] = li; u[i] = ui;
+        y[i] = a.warm ? a.ys[om + i] : 0.0;
+        z[i] = a.warm ? a.zs[om + i] : 0.0;
+        rho_v[i] = brho_of(btype_of(li, ui), rho, a.rho_is_vec, a.rho_eq_factor);
+        w[i] = 0.0;
+      }
+      cta_reduce<2>(v, 3u, s_red, s_tot);
+      nq_s = s_tot[0];
+      nq_t = a.unscale ? s_tot[1] : s_tot[0];
+    }
+    // Jacobi diagonal of K and ax = A x, w2 = rho (z - ax) - y
+    for (int base = 0; base < n; base += NGN) {
+      const int row = base + grp_n;
+      const bool valid = row < n;
+      double ms = a.cg_precond ? brow_dot_sq<LGN>(a.At, rho_v, row, valid, lane_n) : 0.0;
+      ms = group_sum<LGN>(ms);
+      if (valid && lane_n == 0) Minv[row] = a.cg_precond ? 1.0 / (__ldg(a.pdiag + row) + sigma + ms) : 1.0;
+    }
+    for (int base = 0; base < m; base += NGM) {
+      const int row = base + grp_m;
+      const bool valid = row < m;
+      const double acc = group_sum<LGM>(a.warm ? brow_dot<LGM>(a.A, x, row, valid, lane_m) : 0.0);
+      if (valid && lane_m == 0) {
+        ax[row] = acc;
+        w2[row] = rho_v[row] * (z[row] - acc) - y[row];
+      }
+    }
+    __syncthreads();
+
+    int rho_updates = 0, status = 0, k = 0, cg_total = 0;
+    double obj = 0, dobj = 0, gap = 0, prim_res = 0, dual_res = 0, nprim = 0, ndual = 0;
+    double s_prim = 0, s_nprim = 0, s_dual = 0, s_ndual = 0;
+    double ndy = 0, lhs = 0, vu = NEG_INF, vl = NEG_INF, sup = 0;
+    double t_prim = 0, t_ax = 0, t_z = 0;
+    double ndx = 0, qdx = 0;
+    double rz = 0, r0max = 0;
+    bool time_up = false;
+
+    // R phase: r = -(P x + q) + A' w2, p = Minv r; full = also the dual-side residual quantities;
+    // lite = after a rho update (px kept, Jacobi diagonal refreshed)
+    auto phase_R = [&](bool full, bool lite) {
+      double v[BR_K];
+#pragma unroll
+      for (int i = 0; i < BR_K; ++i) v[i] = 0.0;
+      for (int base = 0; base < n; base += NGN) {
+        const int row = base + grp_n;
+        const bool valid = row < n;
+        double pxv = 0, atw = 0, aty = 0, msum = 0;
+        if (lite) {
+          atw = brow_dot<LGN>(a.At, w2, row, valid, lane_n);
+          if (a.cg_precond) msum = brow_dot_sq<LGN>(a.At, rho_v, row, valid, lane_n);
+          msum = group_sum<LGN>(msum);
+        } else {
+          pxv = brow_dot<LGN>(a.P, x, row, valid, lane_n);
+          if (full) brow_dot2<LGN>(a.At, w2, y, row, valid, lane_n, atw, aty);
+          else atw = brow_dot<LGN>(a.At, w2, row, valid, lane_n);
+          pxv = group_sum<LGN>(pxv);
+          if (full) aty = group_sum<LGN>(aty);
+        }
+        atw = group_sum<LGN>(atw);
+        if (valid && lane_n == 0) {
+          const double qj = q[row];
+          if (lite) {
+            pxv = px[row];
+            if (a.cg_precond) Minv[row] = 1.0 / (__ldg(a.pdiag + row) + sigma + msum);
+          }
+          const double rj = -(pxv + qj) + atw;
+          const double pj = Minv[row] * rj;
+          r[row] = rj;
+          p[row] = pj;
+          v[BR_RZ] += rj * pj;
+          v[BR_R0] = nanmax(v[BR_R0], fabs(rj));
+          if (!lite) px[row] = pxv;
+          if (full) {
+            const double xj = x[row], dj = alpha * d[row];
+            const double dres = pxv + qj + aty;
+            const double di = Dinv_t ? __ldg(Dinv_t + row) : 1.0;
+            v[BR_SDUAL] = nanmax(v[BR_SDUAL], fabs(dres));
+            v[BR_SATY] = nanmax(v[BR_SATY], fabs(aty));
+            v[BR_SPX] = nanmax(v[BR_SPX], fabs(pxv));
+            v[BR_TDUAL] = nanmax(v[BR_TDUAL], fabs(di * dres));
+            v[BR_TATY] = nanmax(v[BR_TATY], fabs(di * aty));
+            v[BR_TPX] = nanmax(v[BR_TPX], fabs(di * pxv));
+            v[BR_XPX] += xj * pxv;
+            v[BR_QX] += qj * xj;
+            v[BR_NDX] = nanmax(v[BR_NDX], fabs((D_t ? __ldg(D_t + row) : 1.0) * dj));
+            v[BR_QDX] += qj * dj;
+          }
+        }
+      }
+      if (full && tid == 0) v[BR_TL] = ((double)(global_timer_ns() - t_start) > a.time_limit_ns) ? 1.0 : 0.0;
+      cta_reduce<BR_K>(v, BR_MAXMASK, s_red, s_tot);
+      rz = s_tot[BR_RZ];
+      r0max = s_tot[BR_R0];
+      if (full) {
+        s_dual = s_tot[BR_SDUAL];
+        s_ndual = fmax(fmax(s_tot[BR_SATY], s_tot[BR_SPX]), nq_s);
+        dual_res = cinv_eff * s_tot[BR_TDUAL];
+        ndual = cinv_eff * fmax(fmax(s_tot[BR_TATY], s_tot[BR_TPX]), nq_t);
+        obj = (0.5 * s_tot[BR_XPX] + s_tot[BR_QX]) * cinv;
+        dobj = (-0.5 * s_tot[BR_XPX] - sup) * cinv;
+        gap = obj - dobj;
+        ndx = s_tot[BR_NDX];
+        qdx = s_tot[BR_QDX];
+        time_up = s_tot[BR_TL] > 0.5;
+        prim_res = t_prim;
+        nprim = fmax(t_ax, t_z);
+      }
+    };
+
+    // |Dinv * scale * (M vec)|inf over the n rows (infeasibility certificates)
+    auto cert_norm = [&](const CsrMat& M, const double* vec, double scale) -> double {
+      double v[1] = {0.0};
+      for (int base = 0; base < n; base += NGN) {
+        const int row = base + grp_n;
+        const bool valid = row < n;
+        const double acc = group_sum<LGN>(brow_dot<LGN>(M, vec, row, valid, lane_n));
+        if (valid && lane_n == 0) v[0] = nanmax(v[0], fabs((Dinv_t ? __ldg(Dinv_t + row) : 1.0) * scale * acc));
+      }
+      cta_reduce<1>(v, 1u, s_red, s_tot);
+      return s_tot[0];
+    };
+
+    // termination test (reference: _osqp.py:998-1077); f = 10 -> "inaccurate"
+    auto evaluate = [&](double f) -> int {
+      if (!(prim_res <= QP_INFTY) || !(dual_res <= QP_INFTY)) return 9;
+      const double ea = f * a.eps_abs, er = f * a.eps_rel;
+      const bool prim_ok = (m == 0) || (prim_res < ea + er * nprim);
+      const bool dual_ok = dual_res < ea + er * ndual;
+      const bool gap_ok = !a.check_dualgap || (fabs(gap) < ea + er * fmax(fabs(obj), fabs(dobj)));
+      if (prim_ok && dual_ok && gap_ok) return f > 1.0 ? 2 : 1;
+      if (!prim_ok) {
+        const double eps = f * a.eps_pinf;
+        if (ndy > eps && lhs < -eps * ndy) {
+          const double nat = cert_norm(a.At, w, 1.0);
+          if (nat < eps * ndy) return f > 1.0 ? 4 : 3;
+        }
+      }
+      if (!dual_ok) {
+        const double eps = f * a.eps_dinf;
+        if (ndx > eps && qdx < -c_eff * eps * ndx && vu <= eps * ndx && vl <= eps * ndx) {
+          const double npd = cert_norm(a.P, d, alpha);
+          if (npd < c_eff * eps * ndx) return f > 1.0 ? 6 : 5;
+        }
+      }
+      return 0;
+    };
+
+    // ================================================================ main loop
+    for (;;) {
+      const bool last = (k >= a.max_iter);
+      const bool chk = k > 0 && ((a.check_term > 0 && (k % a.check_term) == 0) || last);
+      const bool adp = k > 0 && !last && a.adaptive_rho && a.adapt_interval > 0 && (k % a.adapt_interval) == 0;
+      const bool full = chk || adp;
+
+      phase_R(full, false);
+      if (chk) {
+        status = evaluate(1.0);
+        if (status) break;
+        if (last) {
+          status = evaluate(10.0);
+          if (!status) status = 7;
+          break;
+        }
+        if (time_up) { status = 8; break; }
+      }
+      if (adp) {   // reference: _osqp.py:880-930 (scaled quantities)
+        const double pr = s_prim / (s_nprim + 1e-10);
+        const double du = s_dual / (s_ndual + 1e-10);
+        double rho_new = rho * sqrt(pr / (du + 1e-10));
+        rho_new = fmin(fmax(rho_new, RHO_MIN), RHO_MAX);
+        if (rho_new > a.adapt_tol * rho || rho_new < rho / a.adapt_tol) {
+          rho = rho_new;
+          rho_updates++;
+          for (int i = tid; i < m; i += NTB) {
+            const double rv = brho_of(btype_of(l[i], u[i]), rho, a.rho_is_vec, a.rho_eq_factor);
+            rho_v[i] = rv;
+            w2[i] = rv * (z[i] - ax[i]) - y[i];
+          }
+          __syncthreads();
+          phase_R(false, true);
+        }
+      }
+
+      // -------------------------------------------------------------- PCG on K d = r
+      bool have_d = false;
+      if (r0max > 1e-150) {
+        const double tol = a.cg_tol_frac * r0max;
+        for (int j = 0; j < a.cg_max_iter; ++j) {
+          // C1: w = rho .* (A p)
+          for (int base = 0; base < m; base += NGM) {
+            const int row = base + grp_m;
+            const bool valid = row < m;
+            const double acc = group_sum<LGM>(brow_dot<LGM>(a.A, p, row, valid, lane_m));
+            if (valid && lane_m == 0) w[row] = rho_v[row] * acc;
+          }
+          __syncthreads();
+          // C2: kp = P p + sigma p + A' w ; <p, kp>
+          double v1[1] = {0.0};
+          for (int base = 0; base < n; base += NGN) {
+            const int row = base + grp_n;
+            const bool valid = row < n;
+            const double acc = group_sum<LGN>(brow_dot<LGN>(a.P, p, row, valid, lane_n) + brow_dot<LGN>(a.At, w, row, valid, lane_n));
+            if (valid && lane_n == 0) {
+              const double pj = p[row];
+              const double kpj = acc + sigma * pj;
+              kp[row] = kpj;
+              v1[0] += pj * kpj;
+            }
+          }
+          cta_reduce<1>(v1, 0u, s_red, s_tot);
+          const double pkp = s_tot[0];
+          if (!(pkp > 0.0)) { status = 9; break; }   // K not positive definite (or NaN): non-convex
+          const double aj = rz / pkp;
+          cg_total++;
+          // C3: d += a p ; r -= a kp ; <r, Minv r> ; |r|inf
+          double v2[2] = {0.0, 0.0};
+          for (int i = tid; i < n; i += NTB) {
+            const double pi = p[i];
+            d[i] = (j == 0) ? aj * pi : fma(aj, pi, d[i]);
+            const double ri = fma(-aj, kp[i], r[i]);
+            r[i] = ri;
+            v2[0] += ri * Minv[i] * ri;
+            v2[1] = nanmax(v2[1], fabs(ri));
+          }
+          have_d = true;
+          cta_reduce<2>(v2, 2u, s_red, s_tot);
+          const double rz_new = s_tot[0], rmax = s_tot[1];
+          if (!(rmax > tol) || j + 1 == a.cg_max_iter) break;
+          // C4: p = Minv r + b p
+          const double bj = rz_new / rz;
+          rz = rz_new;
+          for (int i = tid; i < n; i += NTB) p[i] = fma(bj, p[i], Minv[i] * r[i]);
+          __syncthreads();
+        }
+        if (status) break;
+      }
+      if (!have_d) {
+        for (int i = tid; i < n; i += NTB) d[i] = 0.0;
+        __syncthreads();
+      }
+
+      // -------------------------------------------------------------- Z phase
+      const int kn = k + 1;
+      const bool last_n = (kn >= a.max_iter);
+      const bool full_n = ((a.check_term > 0 && (kn % a.check_term) == 0) || last_n) ||
+                          (!last_n && a.adaptive_rho && a.adapt_interval > 0 && (kn % a.adapt_interval) == 0);
+      {
+        double v[BZ_K];
+#pragma unroll
+        for (int i = 0; i < BZ_K; ++i) v[i] = 0.0;
+        v[BZ_VU] = NEG_INF; v[BZ_VL] = NEG_INF;
+        for (int base = 0; base < m; base += NGM) {
+          const int row = base + grp_m;
+          const bool valid = row < m;
+          const double ad = group_sum<LGM>(brow_dot<LGM>(a.A, d, row, valid, lane_m));
+          if (valid && lane_m == 0) {
+            const double ax_old = ax[row], z_old = z[row], y_old = y[row];
+            const double rv = rho_v[row], ri = 1.0 / rv, li = l[row], ui = u[row];
+            const double zt = ax_old + ad;                                   // z~ = A x~
+            const double zr = alpha * zt + (1.0 - alpha) * z_old;            // _osqp.py:686-690
+            const double zn = fmin(fmax(zr + ri * y_old, li), ui);           // _osqp.py:670-674
+            const double dy = rv * (zr - zn);                                // _osqp.py:698-703
+            const double yn = y_old + dy;
+            const double axn = fma(alpha, ad, ax_old);
+            z[row] = zn; y[row] = yn; ax[row] = axn;
+            w2[row] = rv * (zn - axn) - yn;
+            if (full_n) {
+              const double ei = Einv_t ? __ldg(Einv_t + row) : 1.0;
+              const double pr = axn - zn;
+              v[BZ_SPRIM] = nanmax(v[BZ_SPRIM], fabs(pr));
+              v[BZ_SAX] = nanmax(v[BZ_SAX], fabs(axn));
+              v[BZ_SZ] = nanmax(v[BZ_SZ], fabs(zn));
+              v[BZ_TPRIM] = nanmax(v[BZ_TPRIM], fabs(ei * pr));
+              v[BZ_TAX] = nanmax(v[BZ_TAX], fabs(ei * axn));
+              v[BZ_TZ] = nanmax(v[BZ_TZ], fabs(ei * zn));
+              const bool lfin = li > -INF_THRESH, ufin = ui < INF_THRESH;
+              double dyp = dy;
+              if (!ufin && !lfin) dyp = 0.0;
+              else if (!ufin) dyp = fmin(dy, 0.0);
+              else if (!lfin) dyp = fmax(dy, 0.0);
+              w[row] = dyp;
+              v[BZ_NDY] = nanmax(v[BZ_NDY], fabs((E_t ? __ldg(E_t + row) : 1.0) * dyp));
+              v[BZ_LHS] += (ufin ? ui * fmax(dyp, 0.0) : 0.0) + (lfin ? li * fmin(dyp, 0.0) : 0.0);
+              const double adx = ei * alpha * ad;
+              if (ufin) v[BZ_VU] = nanmax(v[BZ_VU], adx);
+              if (lfin) v[BZ_VL] = nanmax(v[BZ_VL], -adx);
+              v[BZ_SUP] += (ufin ? ui * fmax(yn, 0.0) : 0.0) + (lfin ? li * fmin(yn, 0.0) : 0.0);
+            }
+          }
+        }
+        for (int i = tid; i < n; i += NTB) x[i] = fma(alpha, d[i], x[i]);      // _osqp.py:664-668
+        if (full_n) {
+          cta_reduce<BZ_K>(v, BZ_MAXMASK, s_red, s_tot);
+          s_prim = s_tot[BZ_SPRIM];
+          s_nprim = fmax(s_tot[BZ_SAX], s_tot[BZ_SZ]);
+          t_prim = s_tot[BZ_TPRIM]; t_ax = s_tot[BZ_TAX]; t_z = s_tot[BZ_TZ];
+          ndy = s_tot[BZ_NDY]; lhs = s_tot[BZ_LHS]; vu = s_tot[BZ_VU]; vl = s_tot[BZ_VL]; sup = s_tot[BZ_SUP];
+        } else {
+          __syncthreads();
+        }
+      }
+      k = kn;
+    }
+
+    // ---------------------------------------------------------------- store (reference: _osqp.py:1098-1115)
+    __syncthreads();
+    const int mode = (status == 3 || status == 4) ? 1 : ((status == 5 || status == 6) ? 2 : 0);
+    const bool bad = mode != 0 || status == 9;
+    for (int i = tid; i < n; i += NTB) {
+      const double Di = __ldg(a.D + i);
+      a.xs[on + i] = x[i];
+      a.sol_x[on + i] = bad ? NANV : Di * x[i];
+      a.cert_n[on + i] = mode == 2 ? Di * alpha * d[i] : NANV;
+    }
+    for (int i = tid; i < m; i += NTB) {
+      const double Ei = __ldg(a.E + i);
+      a.ys[om + i] = y[i];
+      a.zs[om + i] = z[i];
+      a.sol_y[om + i] = bad ? NANV : Ei * y[i] * cinv;
+      a.cert_m[om + i] = mode == 1 ? Ei * w[i] : NANV;
+    }
+    if (tid == 0) {
+      BInfo o;
+      o.status = status; o.iter = k; o.rho_updates = rho_updates; o.cg_iters = cg_total;
+      o.obj = mode == 1 ? QP_INFTY : (mode == 2 ? -QP_INFTY : (status == 9 ? NANV : obj));
+      o.dual_obj = mode == 1 ? QP_INFTY : (mode == 2 ? -QP_INFTY : (status == 9 ? NANV : dobj));
+      o.prim_res = prim_res; o.dual_res = dual_res; o.rho = rho;
+      const double pr = s_prim / (s_nprim + 1e-10), du = s_dual / (s_ndual + 1e-10);
+      o.rho_estimate = fmin(fmax(rho * sqrt(pr / (du + 1e-10)), RHO_MIN), RHO_MAX);
+      a.info[qp] = o;
+      a.rho_b[qp] = rho;
+    }
+  }
+}
+
+}  // namespace b200qp

@@ -20,6 +20,7 @@
 #include "admm_kernel.cuh"
 #include "admm_kernel_dist.cuh"
 #include "aux_kernels.cuh"
+#include "internal_view.h"
 #include "spmv_kernels.cuh"
 #include "tiling.h"
 
@@ -825,6 +826,16 @@ b200qp_int b200qp_solve(b200qp_solver* solver) {
   const b200qp_int rc = solve_begin(solver);
   if (rc) return rc;
   return solve_end(solver);
+}
+
+int b200qp_internal_view(const b200qp_solver* solver, b200qp::InternalView* v) {
+  if (!solver || !solver->work || !v) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  const Work* w = W(solver);
+  v->n = w->n; v->m = w->m; v->device = w->device;
+  v->P = w->P.view(); v->A = w->A.view(); v->At = w->At.view();
+  v->pdiag = w->pdiag.p; v->D = w->D.p; v->Dinv = w->Dinv.p; v->E = w->E.p; v->Einv = w->Einv.p;
+  v->c = w->c; v->rho_eq_factor = w->rho_eq_factor;
+  return 0;
 }
 
 b200qp_int b200qp_get_stats(const b200qp_solver* solver, b200qp_stats* stats) {

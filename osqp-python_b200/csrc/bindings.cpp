@@ -169,6 +169,94 @@ class Solver {
   SolutionView sol_{};
 };
 
+// batched solver: `batch` QPs sharing (P, A) (include/b200qp.h: b200qp_batch_*); replaces the reference's
+// thread-pool loop over solver objects (src/osqp/nn/torch.py:128-164, 200-217)
+class BatchSolver {
+ public:
+  BatchSolver(const CscHandle& P, py::object q, const CscHandle& A, py::object l, py::object u, b200qp_int batch,
+              b200qp_int m, b200qp_int n, const b200qp_settings* settings)
+      : batch_(batch), m_(m), n_(n) {
+    darray qc = darray::ensure(q), lc = darray::ensure(l), uc = darray::ensure(u);
+    if (!qc || !lc || !uc || batch <= 0 || qc.size() != (py::ssize_t)batch * n || lc.size() != (py::ssize_t)batch * m ||
+        uc.size() != (py::ssize_t)batch * m)
+      throw py::value_error(std::to_string(B200QP_DATA_VALIDATION_ERROR));
+    b200qp_int status;
+    {
+      py::gil_scoped_release nogil;
+      status = b200qp_batch_setup(&b_, batch, &P.view, qc.data(), &A.view, lc.data(), uc.data(), m, n, settings);
+    }
+    if (status) throw py::value_error(std::to_string(status));
+  }
+  ~BatchSolver() {
+    if (b_) b200qp_batch_cleanup(b_);
+  }
+  BatchSolver(const BatchSolver&) = delete;
+  BatchSolver& operator=(const BatchSolver&) = delete;
+
+  b200qp_int solve() {
+    py::gil_scoped_release nogil;
+    return b200qp_batch_solve(b_);
+  }
+  const b200qp_float* opt_batch(const py::object& o, darray& keep, py::ssize_t len) const {
+    const b200qp_float* p = opt_doubles(o, keep);
+    if (p && keep.size() != (py::ssize_t)batch_ * len) throw py::value_error(std::to_string(B200QP_DATA_VALIDATION_ERROR));
+    return p;
+  }
+  b200qp_int update_data_vec(py::object q, py::object l, py::object u) {
+    darray kq, kl, ku;
+    const b200qp_float* pq = opt_batch(q, kq, n_);
+    const b200qp_float* pl = opt_batch(l, kl, m_);
+    const b200qp_float* pu = opt_batch(u, ku, m_);
+    py::gil_scoped_release nogil;
+    return b200qp_batch_update_data_vec(b_, pq, pl, pu);
+  }
+  b200qp_int warm_start(py::object x, py::object y) {
+    darray kx, ky;
+    const b200qp_float* px = opt_batch(x, kx, n_);
+    const b200qp_float* pyv = opt_batch(y, ky, m_);
+    return b200qp_batch_warm_start(b_, px, pyv);
+  }
+  b200qp_int update_settings(const b200qp_settings& st) {
+    const b200qp_int status = b200qp_batch_update_settings(b_, &st);
+    if (status) throw py::value_error(std::to_string(status));
+    return status;
+  }
+  b200qp_int update_rho(b200qp_float rho) { return b200qp_batch_update_rho(b_, rho); }
+  py::dict solution() const {
+    py::array_t<b200qp_float> x({(py::ssize_t)batch_, (py::ssize_t)n_}), y({(py::ssize_t)batch_, (py::ssize_t)m_});
+    py::array_t<b200qp_float> pc({(py::ssize_t)batch_, (py::ssize_t)m_}), dc({(py::ssize_t)batch_, (py::ssize_t)n_});
+    b200qp_batch_get_solution(b_, x.mutable_data(), y.mutable_data(), pc.mutable_data(), dc.mutable_data());
+    return py::dict("x"_a = x, "y"_a = y, "prim_inf_cert"_a = pc, "dual_inf_cert"_a = dc);
+  }
+  py::dict info() const {
+    std::vector<b200qp_batch_info> v((size_t)batch_);
+    b200qp_batch_get_info(b_, v.data());
+    py::array_t<b200qp_int> status(batch_), iter(batch_), rho_updates(batch_), cg_iter(batch_);
+    py::array_t<b200qp_float> obj(batch_), dobj(batch_), pres(batch_), dres(batch_), rho(batch_), rho_est(batch_);
+    for (b200qp_int i = 0; i < batch_; ++i) {
+      status.mutable_at(i) = v[i].status_val; iter.mutable_at(i) = v[i].iter;
+      rho_updates.mutable_at(i) = v[i].rho_updates; cg_iter.mutable_at(i) = v[i].cg_iter;
+      obj.mutable_at(i) = v[i].obj_val; dobj.mutable_at(i) = v[i].dual_obj_val; pres.mutable_at(i) = v[i].prim_res;
+      dres.mutable_at(i) = v[i].dual_res; rho.mutable_at(i) = v[i].rho; rho_est.mutable_at(i) = v[i].rho_estimate;
+    }
+    return py::dict("status_val"_a = status, "iter"_a = iter, "rho_updates"_a = rho_updates, "cg_iter"_a = cg_iter,
+                    "obj_val"_a = obj, "dual_obj_val"_a = dobj, "prim_res"_a = pres, "dual_res"_a = dres, "rho"_a = rho,
+                    "rho_estimate"_a = rho_est);
+  }
+  py::dict stats() const {
+    b200qp_batch_stats st{};
+    b200qp_batch_get_stats(b_, &st);
+    return py::dict("admm_iters"_a = st.admm_iters, "cg_iters"_a = st.cg_iters, "kernel_ms"_a = st.kernel_ms,
+                    "setup_time"_a = st.setup_time, "update_time"_a = st.update_time, "solve_time"_a = st.solve_time,
+                    "grid"_a = st.grid, "block"_a = st.block, "smem_bytes"_a = st.smem_bytes, "batch"_a = st.batch,
+                    "n"_a = st.n, "m"_a = st.m);
+  }
+
+ private:
+  b200qp_int batch_, m_, n_;
+  b200qp_batch* b_ = nullptr;
+};
+
 }  // namespace
 
 PYBIND11_MODULE(osqp_cuda, mod) {
@@ -318,6 +406,20 @@ PYBIND11_MODULE(osqp_cuda, mod) {
       .def("update_rho", &Solver::update_rho)
       .def("get_settings", &Solver::settings, py::return_value_policy::reference_internal)
       .def("get_stats", &Solver::stats);
+
+  py::class_<BatchSolver>(mod, "OSQPBatchSolver", py::module_local())
+      .def(py::init<const CscHandle&, py::object, const CscHandle&, py::object, py::object, b200qp_int, b200qp_int,
+                    b200qp_int, const b200qp_settings*>(),
+           "P"_a, "q"_a, "A"_a, "l"_a, "u"_a, "batch"_a, "m"_a, "n"_a, "settings"_a)
+      .def("solve", &BatchSolver::solve)
+      .def("update_data_vec", &BatchSolver::update_data_vec, "q"_a.none(true) = py::none(), "l"_a.none(true) = py::none(),
+           "u"_a.none(true) = py::none())
+      .def("warm_start", &BatchSolver::warm_start, "x"_a.none(true) = py::none(), "y"_a.none(true) = py::none())
+      .def("update_settings", &BatchSolver::update_settings)
+      .def("update_rho", &BatchSolver::update_rho)
+      .def("get_solution", &BatchSolver::solution)
+      .def("get_info", &BatchSolver::info)
+      .def("get_stats", &BatchSolver::stats);
 
   // one process driving every rank of a row-partitioned QP (include/b200qp.h: b200qp_dist_*)
   mod.def("dist_connect_local", [](py::list solvers) {

@@ -1,0 +1,17 @@
+// internal_view.h -- library-internal window into a solver's device workspace, shared by the translation
+// units of libb200qp.so (b200qp.cu owns the workspace, b200qp_batch.cu borrows the scaled matrices and the
+// equilibration vectors of its prototype solver).  Not part of include/b200qp.h.
+#pragma once
+#include "../../include/b200qp.h"
+#include "device_common.cuh"
+
+namespace b200qp {
+struct InternalView {
+  int n, m, device;
+  CsrMat P, A, At;                          // scaled: c D P D (full symmetric CSR), E A D, D A' E
+  const double *pdiag, *D, *Dinv, *E, *Einv;
+  double c, rho_eq_factor;
+};
+}  // namespace b200qp
+
+extern "C" int b200qp_internal_view(const b200qp_solver* solver, b200qp::InternalView* view);

@@ -15,3 +15,4 @@ from osqp.interface import (  # noqa: F401
     constant,
     default_algebra,
 )
+from osqp.batch import OSQPBatch  # noqa: F401,E402  (batched front end, BASELINE.json configs[4])
