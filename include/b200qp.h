@@ -219,7 +219,8 @@ b200qp_int b200qp_dist_solve_group(b200qp_solver **group, b200qp_int world);
 
 /* ---- batched independent QPs (BASELINE.json configs[4]; SURVEY.md 8e "replicas only") ------------------
  * `batch` QPs that share one (P, A) and differ in q, l, u; one CTA per QP, every vector of a QP in shared
- * memory.  Replaces the reference's batched caller, which loops solver objects over a thread pool and
+ * memory (and, for n up to ~150, the inverse of the reduced KKT matrix too, so the inner solve is one dense
+ * mat-vec; larger QPs use the engine's Jacobi-PCG).  Replaces the reference's batched caller, which loops solver objects over a thread pool and
  * re-uses one setup through update() (src/osqp/nn/torch.py:128-164, 200-217): element b is the QP a
  * reference user gets from setup(P, q[0], A, l[0], u[0]) followed by update(q=q[b], l=l[b], u=u[b]) and
  * solve() -- same scaling (D, E, c of element 0; update() never re-equilibrates, _osqp.py:1312-1367), own
@@ -236,6 +237,7 @@ typedef struct {
   double kernel_ms;                 /* device time of the batch kernel, CUDA events on its stream */
   double setup_time, update_time, solve_time; /* host wall clock, seconds */
   b200qp_int grid, block, smem_bytes, batch, n, m;
+  b200qp_int dense;                 /* 1: K^-1 held in shared memory (small QPs); 0: Jacobi-PCG */
 } b200qp_batch_stats;
 b200qp_int b200qp_batch_setup(b200qp_batch **batchp, b200qp_int batch, const b200qp_csc *P, const b200qp_float *q,
                               const b200qp_csc *A, const b200qp_float *l, const b200qp_float *u, b200qp_int m,

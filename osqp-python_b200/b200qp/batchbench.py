@@ -11,6 +11,24 @@ EPS = 1e-4
 KW = dict(eps_abs=EPS, eps_rel=EPS, max_iter=4000, warm_starting=False)
 
 
+def shard_range(batch, rank, world):
+    """QPs [lo, hi) of rank `rank`: contiguous, sizes differ by at most one, no collective needed."""
+    base, extra = divmod(batch, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def reduce_counts(dev_ms, wall_ms, counts, dist=None, torch=None, device=None):
+    """Whole-job numbers from per-rank ones: time = max over ranks, counters = sum over ranks."""
+    if dist is None:
+        return dev_ms, wall_ms, np.asarray(counts, dtype=np.float64)
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    c = torch.tensor(np.asarray(counts, dtype=np.float64), dtype=torch.float64, device=device)
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    return float(t[0]), float(t[1]), c.cpu().numpy()
+
+
 def cpu_sample(P, q, A, l, u, count=16):
     """The reference's way on one host core: one setup, then update(l, u) + cold solve per QP (oracle port of
     the reference algorithm, direct KKT factorisation as in its qdldl path)."""
@@ -32,9 +50,7 @@ def cpu_sample(P, q, A, l, u, count=16):
 def batch_line(args, rank=0, world=1, local=0, dist=None, torch=None, with_cpu=True):
     import osqp
     from b200qp import problems
-    per = BATCH // world
-    lo = rank * per
-    hi = BATCH if rank == world - 1 else lo + per
+    lo, hi = shard_range(BATCH, rank, world)
     P, q, A, l_all, u_all = problems.mpc_batch(BATCH, seed0=4)
     _, _, _, l_alt, u_alt = problems.mpc_batch(BATCH, seed0=4 + BATCH)
     sets = [(np.ascontiguousarray(l_all[lo:hi]), np.ascontiguousarray(u_all[lo:hi])),
@@ -67,14 +83,8 @@ def batch_line(args, rank=0, world=1, local=0, dist=None, torch=None, with_cpu=T
         dev_ms += st["kernel_ms"]; iters += st["admm_iters"]; cg += st["cg_iters"]
         solved += int((res.info.status_val == 1).sum())
     sync()
-    tot = np.array([iters, cg, solved], dtype=np.float64)
-    if dist is not None:
-        t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=torch.device("cuda", local))
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms = float(t[0]), float(t[1])
-        c = torch.tensor(tot, dtype=torch.float64, device=torch.device("cuda", local))
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        tot = c.cpu().numpy()
+    device = torch.device("cuda", local) if dist is not None else None
+    dev_ms, wall_ms, tot = reduce_counts(dev_ms, wall_ms, [iters, cg, solved], dist, torch, device)
     n, m = prob.n, prob.m
     nnz = int(sparse_nnz(P) + 2 * A.nnz)
     line = {

@@ -14,13 +14,21 @@
 //   * the shared matrices are read through L1 (__ldg): all CTAs of an SM walk the same 30 KB;
 //   * phases are separated by __syncthreads, reductions are CTA-level and fixed-order (deterministic);
 //   * CTAs pull QP indices from a global counter, so QPs that need 25 and 200 iterations balance out.
+// Two inner solvers (template flag DENSE):
+//   * DENSE = false: the engine's Jacobi-PCG, as in admm_kernel.cuh (any n, m whose vectors fit shared memory);
+//   * DENSE = true : small QPs (n <= ~150).  K is formed and inverted IN SHARED MEMORY once per rho value
+//     (in-place Gauss-Jordan; K is SPD so no pivoting, a non-positive pivot = NON_CVX) and the PCG is replaced by
+//     one dense mat-vec d = K^-1 r per ADMM iteration -- 3 CTA barriers per iteration instead of ~30.  The
+//     residual-correction form keeps the step exact to the accuracy of K^-1 relative to the correction d, not x.
+//     This is the reference's "factor once, solve every iteration" scheme (src/osqppurepy/_osqp.py:281-312,
+//     refactor on rho update :1597) with the factorisation held on chip.
 #pragma once
 #include "device_common.cuh"
 
 namespace b200qp {
 
-constexpr int NTB = 256;        // threads per CTA of the batch kernel
-constexpr int NWB = NTB / 32;
+constexpr int NTB_PCG = 256;    // threads per CTA, PCG mode (4 CTAs per SM)
+constexpr int NTB_DENSE = 512;  // threads per CTA, dense mode (1 CTA per SM: K^-1 takes most of the shared memory)
 
 struct BInfo {                  // per QP, written at exit (64 bytes)
   int status, iter, rho_updates, cg_iters;
@@ -42,7 +50,7 @@ struct BArgs {
 };
 
 // CTA reduction of K slots (sum or NaN-propagating max per maxmask bit); result in s_tot[0..K)
-template <int K>
+template <int K, int NWB>
 __device__ __forceinline__ void cta_reduce(double (&v)[K], unsigned maxmask, double* s_red, double* s_tot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -111,12 +119,18 @@ enum { BZ_SPRIM = 0, BZ_SAX, BZ_SZ, BZ_TPRIM, BZ_TAX, BZ_TZ, BZ_NDY, BZ_LHS, BZ_
 constexpr unsigned BZ_MAXMASK = (1u << BZ_SPRIM) | (1u << BZ_SAX) | (1u << BZ_SZ) | (1u << BZ_TPRIM) | (1u << BZ_TAX) |
                                 (1u << BZ_TZ) | (1u << BZ_NDY) | (1u << BZ_VU) | (1u << BZ_VL);
 
-inline size_t batch_smem_bytes(int n, int m) {
-  return ((size_t)8 * n + (size_t)8 * m + KMAX * NWB + KMAX) * sizeof(double);
+inline int batch_ldk(int n) { return n | 1; }                    // odd row stride of K^-1: column reads conflict-free
+inline int batch_npad(int n) { return (n + 31) & ~31; }
+inline size_t batch_smem_bytes(int n, int m, bool dense) {
+  const int nt = dense ? NTB_DENSE : NTB_PCG;
+  size_t d = (size_t)8 * n + (size_t)8 * m + KMAX * (nt / 32) + KMAX;
+  if (dense) d += (size_t)n * batch_ldk(n) + 2 * (size_t)n + (size_t)(nt / batch_npad(n)) * batch_npad(n);
+  return d * sizeof(double);
 }
 
-template <int LGN, int LGM>
-__global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constant__ BArgs a) {
+template <int LGN, int LGM, int NTB, bool DENSE>
+__global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __grid_constant__ BArgs a) {
+  constexpr int NWB = NTB / 32;
   extern __shared__ double sm[];
   __shared__ int s_qp;
   const int n = a.n, m = a.m, tid = threadIdx.x;
@@ -138,6 +152,13 @@ __global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constan
   double* const rho_v = w + m;
   double* const s_red = rho_v + m;
   double* const s_tot = s_red + KMAX * NWB;
+  // dense mode: K^-1 (n x LDK), pivot row / column of the elimination step, partial sums of the mat-vec
+  const int LDK = n | 1, npad = (n + 31) & ~31, PARTS = DENSE ? NTB / npad : 1;
+  double* const Kinv = s_tot + KMAX;
+  double* const rowk = Kinv + (DENSE ? n * LDK : 0);
+  double* const colk = rowk + (DENSE ? n : 0);
+  double* const partbuf = colk + (DENSE ? n : 0);
+  const int tj = tid % npad, ti0 = tid / npad;
 
   constexpr int NGN = NTB / LGN, NGM = NTB / LGM;
   const int lane_n = tid & (LGN - 1), grp_n = tid / LGN;
@@ -182,7 +203,7 @@ __global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constan
         rho_v[i] = brho_of(btype_of(li, ui), rho, a.rho_is_vec, a.rho_eq_factor);
         w[i] = 0.0;
       }
-      cta_reduce<2>(v, 3u, s_red, s_tot);
+      cta_reduce<2, NWB>(v, 3u, s_red, s_tot);
       nq_s = s_tot[0];
       nq_t = a.unscale ? s_tot[1] : s_tot[0];
     }
@@ -190,9 +211,10 @@ __global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constan
     for (int base = 0; base < n; base += NGN) {
       const int row = base + grp_n;
       const bool valid = row < n;
-      double ms = a.cg_precond ? brow_dot_sq<LGN>(a.At, rho_v, row, valid, lane_n) : 0.0;
+      const bool jac = a.cg_precond && !DENSE;
+      double ms = jac ? brow_dot_sq<LGN>(a.At, rho_v, row, valid, lane_n) : 0.0;
       ms = group_sum<LGN>(ms);
-      if (valid && lane_n == 0) Minv[row] = a.cg_precond ? 1.0 / (__ldg(a.pdiag + row) + sigma + ms) : 1.0;
+      if (valid && lane_n == 0) Minv[row] = jac ? 1.0 / (__ldg(a.pdiag + row) + sigma + ms) : 1.0;
     }
     for (int base = 0; base < m; base += NGM) {
       const int row = base + grp_m;
@@ -214,6 +236,70 @@ __global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constan
     double rz = 0, r0max = 0;
     bool time_up = false;
 
+    // ---- dense mode: K = P + sigma I + A' rho A formed row by row (thread j owns row j: no atomics), inverted
+    // in place by Gauss-Jordan elimination without pivoting (K is SPD; a non-positive pivot means it is not)
+    auto build_inverse = [&]() -> bool {
+      for (int e = tid; e < n * LDK; e += NTB) Kinv[e] = 0.0;
+      __syncthreads();
+      if (tid < n) {
+        double* Kj = Kinv + tid * LDK;
+        for (int k = __ldg(a.P.ptr + tid); k < __ldg(a.P.ptr + tid + 1); ++k) Kj[__ldg(a.P.idx + k)] += __ldg(a.P.val + k);
+        Kj[tid] += sigma;
+        for (int t = __ldg(a.At.ptr + tid); t < __ldg(a.At.ptr + tid + 1); ++t) {
+          const int i = __ldg(a.At.idx + t);
+          const double f = rho_v[i] * __ldg(a.At.val + t);
+          for (int k = __ldg(a.A.ptr + i); k < __ldg(a.A.ptr + i + 1); ++k) {
+            const int c = __ldg(a.A.idx + k);
+            Kj[c] = fma(f, __ldg(a.A.val + k), Kj[c]);
+          }
+        }
+      }
+      __syncthreads();
+      bool ok = true;
+      for (int k = 0; k < n; ++k) {
+        const double akk = Kinv[k * LDK + k];
+        ok = ok && (akk > 0.0);
+        const double piv = 1.0 / akk;
+        if (ti0 == 0 && tj < n) { rowk[tj] = Kinv[k * LDK + tj] * piv; colk[tj] = Kinv[tj * LDK + k]; }
+        __syncthreads();
+        if (tj < n && ti0 < PARTS) {
+          const double rj = rowk[tj];
+          for (int i = ti0; i < n; i += PARTS) {
+            double v;
+            if (i == k) v = (tj == k) ? piv : rj;
+            else if (tj == k) v = -colk[i] * piv;
+            else v = fma(-colk[i], rj, Kinv[i * LDK + tj]);
+            Kinv[i * LDK + tj] = v;
+          }
+        }
+        __syncthreads();
+      }
+      return ok;
+    };
+    // d = K^-1 r  (K^-1 symmetric: thread (part, j) walks column j = row j with unit-stride lanes)
+    auto dense_apply = [&]() {
+      if (tj < n && ti0 < PARTS) {
+        double acc0 = 0.0, acc1 = 0.0;
+        int t = ti0;
+        for (; t + PARTS < n; t += 2 * PARTS) {
+          acc0 = fma(Kinv[t * LDK + tj], r[t], acc0);
+          acc1 = fma(Kinv[(t + PARTS) * LDK + tj], r[t + PARTS], acc1);
+        }
+        if (t < n) acc0 = fma(Kinv[t * LDK + tj], r[t], acc0);
+        partbuf[ti0 * npad + tj] = acc0 + acc1;
+      }
+      __syncthreads();
+      if (tid < n) {
+        double sacc = partbuf[tid];
+        for (int pp = 1; pp < PARTS; ++pp) sacc += partbuf[pp * npad + tid];
+        d[tid] = sacc;
+      }
+      __syncthreads();
+    };
+    if (DENSE) {
+      if (!build_inverse()) status = 9;
+    }
+
     // R phase: r = -(P x + q) + A' w2, p = Minv r; full = also the dual-side residual quantities;
     // lite = after a rho update (px kept, Jacobi diagonal refreshed)
     auto phase_R = [&](bool full, bool lite) {
@@ -226,7 +312,7 @@ __global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constan
         double pxv = 0, atw = 0, aty = 0, msum = 0;
         if (lite) {
           atw = brow_dot<LGN>(a.At, w2, row, valid, lane_n);
-          if (a.cg_precond) msum = brow_dot_sq<LGN>(a.At, rho_v, row, valid, lane_n);
+          if (a.cg_precond && !DENSE) msum = brow_dot_sq<LGN>(a.At, rho_v, row, valid, lane_n);
           msum = group_sum<LGN>(msum);
         } else {
           pxv = brow_dot<LGN>(a.P, x, row, valid, lane_n);
@@ -240,7 +326,7 @@ __global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constan
           const double qj = q[row];
           if (lite) {
             pxv = px[row];
-            if (a.cg_precond) Minv[row] = 1.0 / (__ldg(a.pdiag + row) + sigma + msum);
+            if (a.cg_precond && !DENSE) Minv[row] = 1.0 / (__ldg(a.pdiag + row) + sigma + msum);
           }
           const double rj = -(pxv + qj) + atw;
           const double pj = Minv[row] * rj;
@@ -267,7 +353,7 @@ __global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constan
         }
       }
       if (full && tid == 0) v[BR_TL] = ((double)(global_timer_ns() - t_start) > a.time_limit_ns) ? 1.0 : 0.0;
-      cta_reduce<BR_K>(v, BR_MAXMASK, s_red, s_tot);
+      cta_reduce<BR_K, NWB>(v, BR_MAXMASK, s_red, s_tot);
       rz = s_tot[BR_RZ];
       r0max = s_tot[BR_R0];
       if (full) {
@@ -295,7 +381,7 @@ __global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constan
         const double acc = group_sum<LGN>(brow_dot<LGN>(M, vec, row, valid, lane_n));
         if (valid && lane_n == 0) v[0] = nanmax(v[0], fabs((Dinv_t ? __ldg(Dinv_t + row) : 1.0) * scale * acc));
       }
-      cta_reduce<1>(v, 1u, s_red, s_tot);
+      cta_reduce<1, NWB>(v, 1u, s_red, s_tot);
       return s_tot[0];
     };
 
@@ -325,7 +411,7 @@ __global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constan
     };
 
     // ================================================================ main loop
-    for (;;) {
+    for (; status == 0;) {
       const bool last = (k >= a.max_iter);
       const bool chk = k > 0 && ((a.check_term > 0 && (k % a.check_term) == 0) || last);
       const bool adp = k > 0 && !last && a.adaptive_rho && a.adapt_interval > 0 && (k % a.adapt_interval) == 0;
@@ -356,13 +442,16 @@ __global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constan
             w2[i] = rv * (z[i] - ax[i]) - y[i];
           }
           __syncthreads();
+          if (DENSE && !build_inverse()) { status = 9; break; }
           phase_R(false, true);
         }
       }
 
       // -------------------------------------------------------------- PCG on K d = r
       bool have_d = false;
-      if (r0max > 1e-150) {
+      if (DENSE) {
+        if (r0max > 1e-150) { dense_apply(); have_d = true; }
+      } else if (r0max > 1e-150) {
         const double tol = a.cg_tol_frac * r0max;
         for (int j = 0; j < a.cg_max_iter; ++j) {
           // C1: w = rho .* (A p)
@@ -386,7 +475,7 @@ __global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constan
               v1[0] += pj * kpj;
             }
           }
-          cta_reduce<1>(v1, 0u, s_red, s_tot);
+          cta_reduce<1, NWB>(v1, 0u, s_red, s_tot);
           const double pkp = s_tot[0];
           if (!(pkp > 0.0)) { status = 9; break; }   // K not positive definite (or NaN): non-convex
           const double aj = rz / pkp;
@@ -402,7 +491,7 @@ __global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constan
             v2[1] = nanmax(v2[1], fabs(ri));
           }
           have_d = true;
-          cta_reduce<2>(v2, 2u, s_red, s_tot);
+          cta_reduce<2, NWB>(v2, 2u, s_red, s_tot);
           const double rz_new = s_tot[0], rmax = s_tot[1];
           if (!(rmax > tol) || j + 1 == a.cg_max_iter) break;
           // C4: p = Minv r + b p
@@ -469,7 +558,7 @@ __global__ void __launch_bounds__(NTB, 4) admm_batch_kernel(const __grid_constan
         }
         for (int i = tid; i < n; i += NTB) x[i] = fma(alpha, d[i], x[i]);      // _osqp.py:664-668
         if (full_n) {
-          cta_reduce<BZ_K>(v, BZ_MAXMASK, s_red, s_tot);
+          cta_reduce<BZ_K, NWB>(v, BZ_MAXMASK, s_red, s_tot);
           s_prim = s_tot[BZ_SPRIM];
           s_nprim = fmax(s_tot[BZ_SAX], s_tot[BZ_SZ]);
           t_prim = s_tot[BZ_TPRIM]; t_ax = s_tot[BZ_TAX]; t_z = s_tot[BZ_TZ];

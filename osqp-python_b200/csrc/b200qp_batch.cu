@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -63,11 +64,17 @@ __global__ void kb_spmv(CsrMat A, int batch, const double* __restrict__ xs, doub
 
 typedef void (*batch_fn)(const BArgs);
 int pick_blg(double avg) { return avg <= 12.0 ? 4 : 16; }
-batch_fn pick_batch_kernel(int lgn, int lgm) {
-  if (lgn == 4 && lgm == 4) return admm_batch_kernel<4, 4>;
-  if (lgn == 4 && lgm == 16) return admm_batch_kernel<4, 16>;
-  if (lgn == 16 && lgm == 4) return admm_batch_kernel<16, 4>;
-  return admm_batch_kernel<16, 16>;
+batch_fn pick_batch_kernel(int lgn, int lgm, bool dense) {
+  if (dense) {
+    if (lgn == 4 && lgm == 4) return admm_batch_kernel<4, 4, NTB_DENSE, true>;
+    if (lgn == 4 && lgm == 16) return admm_batch_kernel<4, 16, NTB_DENSE, true>;
+    if (lgn == 16 && lgm == 4) return admm_batch_kernel<16, 4, NTB_DENSE, true>;
+    return admm_batch_kernel<16, 16, NTB_DENSE, true>;
+  }
+  if (lgn == 4 && lgm == 4) return admm_batch_kernel<4, 4, NTB_PCG, false>;
+  if (lgn == 4 && lgm == 16) return admm_batch_kernel<4, 16, NTB_PCG, false>;
+  if (lgn == 16 && lgm == 4) return admm_batch_kernel<16, 4, NTB_PCG, false>;
+  return admm_batch_kernel<16, 16, NTB_PCG, false>;
 }
 
 }  // namespace
@@ -87,7 +94,8 @@ struct b200qp_batch {
   // pinned host mirrors of the last solve
   double *h_x = nullptr, *h_y = nullptr, *h_cn = nullptr, *h_cm = nullptr;
   BInfo* h_info = nullptr;
-  int lgn = 4, lgm = 4, grid = 1;
+  int lgn = 4, lgm = 4, grid = 1, nt = NTB_PCG;
+  bool dense = false;
   size_t smem = 0;
   bool solved = false;
   b200qp_batch_stats stats{};
@@ -196,22 +204,27 @@ b200qp_int b200qp_batch_setup(b200qp_batch** batchp, b200qp_int batch, const b20
     // launch geometry: every vector of one QP in shared memory
     b->lgn = pick_blg(n ? (double)(b->v.P.nnz + b->v.At.nnz) / n / 2 : 1.0);
     b->lgm = pick_blg(m ? (double)b->v.A.nnz / m : 1.0);
-    b->smem = batch_smem_bytes(n, m);
     cudaDeviceProp prop;
     BCK(cudaGetDeviceProperties(&prop, b->device));
+    // inner solver: K^-1 on chip when it fits next to the vectors (small QPs), else the engine's PCG.
+    // B200QP_BATCH_DENSE=0 / 1 forces the choice (1 still requires that it fits).
+    b->dense = batch_smem_bytes(n, m, true) <= (size_t)prop.sharedMemPerBlockOptin;
+    if (const char* e = std::getenv("B200QP_BATCH_DENSE")) b->dense = b->dense && std::atoi(e) != 0;
+    b->smem = batch_smem_bytes(n, m, b->dense);
+    b->nt = b->dense ? NTB_DENSE : NTB_PCG;
     if (b->smem > (size_t)prop.sharedMemPerBlockOptin) {
       std::fprintf(stderr, "[b200qp] batch: n = %d, m = %d needs %zu bytes of shared memory per QP (limit %zu); "
                            "use one b200qp_solver per QP for problems of this size\n",
                    n, m, b->smem, (size_t)prop.sharedMemPerBlockOptin);
       throw (int)B200QP_MEM_ALLOC_ERROR;
     }
-    batch_fn fn = pick_batch_kernel(b->lgn, b->lgm);
+    batch_fn fn = pick_batch_kernel(b->lgn, b->lgm, b->dense);
     BCK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     int occ = 0;
-    BCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, NTB, b->smem));
+    BCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, b->nt, b->smem));
     if (occ < 1) throw (int)B200QP_ALGEBRA_LOAD_ERROR;
     b->grid = std::min(batch, occ * prop.multiProcessorCount);
-    b->stats.grid = b->grid; b->stats.block = NTB; b->stats.smem_bytes = (int)b->smem;
+    b->stats.grid = b->grid; b->stats.block = b->nt; b->stats.smem_bytes = (int)b->smem; b->stats.dense = b->dense ? 1 : 0;
     b->stats.batch = batch; b->stats.n = n; b->stats.m = m;
   } catch (int code) {
     delete b;
@@ -219,8 +232,8 @@ b200qp_int b200qp_batch_setup(b200qp_batch** batchp, b200qp_int batch, const b20
   }
   b->stats.setup_time = now_s() - t0;
   if (settings->verbose) {
-    std::printf("b200qp batch: %d QPs, n = %d, m = %d, nnz(P) + nnz(A) = %d; grid %d x %d, %zu B shared memory per QP\n",
-                batch, n, m, P->p[n] + A->p[n], b->grid, NTB, b->smem);
+    std::printf("b200qp batch: %d QPs, n = %d, m = %d, nnz(P) + nnz(A) = %d; %s, grid %d x %d, %zu B shared memory per QP\n",
+                batch, n, m, P->p[n] + A->p[n], b->dense ? "on-chip K^-1" : "Jacobi-PCG", b->grid, b->nt, b->smem);
     std::fflush(stdout);
   }
   *batchp = b;
@@ -251,9 +264,9 @@ b200qp_int b200qp_batch_solve(b200qp_batch* b) {
     a.rho_is_vec = st->rho_is_vec; a.check_dualgap = st->check_dualgap;
     a.warm = st->warm_starting ? 1 : 0;
     BCK(cudaMemsetAsync(b->next, 0, sizeof(int), b->stream));
-    batch_fn fn = pick_batch_kernel(b->lgn, b->lgm);
+    batch_fn fn = pick_batch_kernel(b->lgn, b->lgm, b->dense);
     BCK(cudaEventRecord(b->ev0, b->stream));
-    fn<<<b->grid, NTB, b->smem, b->stream>>>(a);
+    fn<<<b->grid, b->nt, b->smem, b->stream>>>(a);
     BCK(cudaEventRecord(b->ev1, b->stream));
     BCK(cudaGetLastError());
     const size_t bn = (size_t)b->batch * b->n, bm = (size_t)b->batch * b->m;

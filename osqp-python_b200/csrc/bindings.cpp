@@ -249,7 +249,7 @@ class BatchSolver {
     return py::dict("admm_iters"_a = st.admm_iters, "cg_iters"_a = st.cg_iters, "kernel_ms"_a = st.kernel_ms,
                     "setup_time"_a = st.setup_time, "update_time"_a = st.update_time, "solve_time"_a = st.solve_time,
                     "grid"_a = st.grid, "block"_a = st.block, "smem_bytes"_a = st.smem_bytes, "batch"_a = st.batch,
-                    "n"_a = st.n, "m"_a = st.m);
+                    "n"_a = st.n, "m"_a = st.m, "dense"_a = st.dense);
   }
 
  private:

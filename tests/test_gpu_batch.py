@@ -5,7 +5,8 @@ Element b of a batch must be the QP a reference user gets from setup(P, q[0], A,
 l=l[b], u=u[b]), solve() (src/osqp/nn/torch.py:128-164 re-uses solvers exactly like that).  Checked against
   * the CPU oracle run live through that same call sequence (direct mode, the pinned one): x*, y*, obj within
     1e-6 relative at eps 1e-9 (BASELINE.json north_star);
-  * the single-QP engine (osqp.OSQP) through that call sequence: same status and iteration count;
+  * the single-QP engine (osqp.OSQP) through that call sequence: same status and iteration count (PCG mode),
+    and the oracle's direct mode with the engine's rho ratio: same iteration count (on-chip K^-1 mode);
   * size-independent properties at the full 8192 x (n=120, m=240): every element solved, KKT residuals of the
     returned (x, y) below the termination tolerance, bitwise determinism between two runs.
 """
@@ -16,6 +17,13 @@ from scipy import sparse
 pytestmark = pytest.mark.gpu
 
 REL = 1e-6
+
+
+@pytest.fixture(params=["dense", "pcg"])
+def mode(request, monkeypatch):
+    """Both inner solvers of the batch kernel: K^-1 in shared memory (default for small QPs) and Jacobi-PCG."""
+    monkeypatch.setenv("B200QP_BATCH_DENSE", "1" if request.param == "dense" else "0")
+    return request.param
 
 
 def _rel(a, b):
@@ -29,7 +37,7 @@ def _oracle_element(P, q0, A, l0, u0, q, l, u, **kw):
     return s.solve()
 
 
-def test_mpc_batch_matches_oracle_tight():
+def test_mpc_batch_matches_oracle_tight(mode):
     import osqp
     from b200qp import problems
     B = 12
@@ -38,6 +46,7 @@ def test_mpc_batch_matches_oracle_tight():
     prob = osqp.OSQPBatch()
     prob.setup(P, q, A, l, u, verbose=False, cg_tol_fraction=1e-3, **kw)
     res = prob.solve()
+    assert prob.stats()["dense"] == (1 if mode == "dense" else 0)
     assert res.x.shape == (B, 120) and res.y.shape == (B, 240)
     for b in range(B):
         ora = _oracle_element(P, q, A, l[0], u[0], q, l[b], u[b], **kw)
@@ -47,11 +56,33 @@ def test_mpc_batch_matches_oracle_tight():
         assert abs(res.info.obj_val[b] - ora.info.obj_val) <= REL * max(1.0, abs(ora.info.obj_val))
 
 
-def test_mpc_batch_matches_single_engine():
-    """Same iteration counts and results as looping the single-QP engine the way the reference's batched
-    caller does: one setup, update(l, u), cold-start solve."""
+def test_mpc_batch_dense_matches_direct_oracle_iterations():
+    """On-chip K^-1 mode is an exact inner solve like the reference's factorisation: same iteration counts and
+    rho updates as the oracle's direct mode (run with the engine's equality-row rho ratio)."""
     import osqp
     from b200qp import problems
+    B = 16
+    P, q, A, l, u = problems.mpc_batch(B)
+    prob = osqp.OSQPBatch()
+    prob.setup(P, q, A, l, u, verbose=False, warm_starting=False)
+    res = prob.solve()
+    st = prob.stats()
+    assert st["dense"] == 1 and st["block"] == 512 and st["cg_iters"] == 0 and st["kernel_ms"] > 0
+    for b in range(B):
+        ora = _oracle_element(P, q, A, l[0], u[0], q, l[b], u[b], rho_eq_factor=10.0)
+        assert res.info.status[b] == ora.info.status == "solved"
+        assert res.info.iter[b] == ora.info.iter, (b, res.info.iter[b], ora.info.iter)
+        assert res.info.rho_updates[b] == ora.info.rho_updates
+        assert _rel(res.x[b], ora.x) < 1e-7 and _rel(res.y[b], ora.y) < 1e-7
+        assert abs(res.info.obj_val[b] - ora.info.obj_val) < 1e-8 * max(1.0, abs(ora.info.obj_val))
+
+
+def test_mpc_batch_matches_single_engine(monkeypatch):
+    """PCG mode: same iteration counts and results as looping the single-QP engine the way the reference's
+    batched caller does: one setup, update(l, u), cold-start solve."""
+    import osqp
+    from b200qp import problems
+    monkeypatch.setenv("B200QP_BATCH_DENSE", "0")
     B = 24
     P, q, A, l, u = problems.mpc_batch(B)
     prob = osqp.OSQPBatch()
@@ -73,7 +104,7 @@ def test_mpc_batch_matches_single_engine():
     assert st["kernel_ms"] > 0 and st["block"] == 256
 
 
-def test_random_batch_with_q_and_onesided_bounds():
+def test_random_batch_with_q_and_onesided_bounds(mode):
     import osqp
     from b200qp import problems
     B, n, m = 9, 60, 90
@@ -94,7 +125,7 @@ def test_random_batch_with_q_and_onesided_bounds():
         assert abs(res.info.obj_val[b] - ora.info.obj_val) <= REL * max(1.0, abs(ora.info.obj_val))
 
 
-def test_update_and_warm_start():
+def test_update_and_warm_start(mode):
     import osqp
     from b200qp import problems
     B = 8
@@ -127,7 +158,7 @@ def test_update_and_warm_start():
     assert ei.value == osqp.SolverError.OSQP_DATA_VALIDATION_ERROR
 
 
-def test_infeasible_element_is_isolated():
+def test_infeasible_element_is_isolated(mode):
     """One primal-infeasible and one dual-infeasible element must not disturb their neighbours."""
     import osqp
     n = 2
@@ -153,7 +184,7 @@ def test_infeasible_element_is_isolated():
     assert np.all(np.isnan(res.prim_inf_cert[0])) and np.all(np.isnan(res.dual_inf_cert[0]))
 
 
-def test_full_config5_properties():
+def test_full_config5_properties(mode):
     """8192 x (n = 120, m = 240): size-independent checks."""
     import osqp
     from b200qp import problems
@@ -196,3 +227,22 @@ def test_batch_too_large_for_shared_memory_fails_loudly():
     with pytest.raises(osqp.OSQPException) as ei:
         prob.setup(P, q, A, l, u, batch=2, verbose=False)
     assert ei.value == osqp.SolverError.OSQP_MEM_ALLOC_ERROR
+
+
+def test_mid_size_batch_falls_back_to_pcg():
+    """n = 400 does not fit K^-1 in shared memory: the batch uses the PCG kernel and still matches the oracle."""
+    import osqp
+    from b200qp import problems
+    B, n, m = 5, 400, 500
+    P, q0, A, l0, u0 = problems.random_qp(n, m, nnz_per_row=5, seed=21, eq_frac=0.1)
+    rng = np.random.default_rng(8)
+    q = q0 + 0.1 * rng.standard_normal((B, n))
+    kw = dict(eps_abs=1e-9, eps_rel=1e-9, max_iter=50000)
+    prob = osqp.OSQPBatch()
+    prob.setup(P, q, A, l0, u0, verbose=False, cg_tol_fraction=1e-3, **kw)
+    res = prob.solve()
+    assert prob.stats()["dense"] == 0 and prob.stats()["block"] == 256
+    for b in range(B):
+        ora = _oracle_element(P, q[0], A, l0, u0, q[b], l0, u0, **kw)
+        assert res.info.status[b] == "solved" and ora.info.status == "solved"
+        assert _rel(res.x[b], ora.x) < REL and _rel(res.y[b], ora.y) < 10 * REL

@@ -39,6 +39,12 @@ def _worker(rank, world, port, q):
         ok_cover = False
     except RuntimeError:
         pass
+    # config-5 sharding (b200qp/batchbench.py): ranges tile [0, batch), counters sum, times max
+    from b200qp import batchbench
+    lo_b, hi_b = batchbench.shard_range(8191, rank, world)
+    dev_ms, wall_ms, tot = batchbench.reduce_counts(3.0 + rank, 7.0 - rank, [hi_b - lo_b, 10 * (rank + 1), 1], dist, torch,
+                                                    torch.device("cpu"))
+    assert (dev_ms, wall_ms) == (4.0, 7.0) and list(tot) == [8191.0, 30.0, 2.0], (dev_ms, wall_ms, tot)
     q.put((rank, out, t.numpy(), ok_cover))
     dist.barrier()
     dist.destroy_process_group()
@@ -62,6 +68,18 @@ def test_gather_slabs_world2_gloo():
         np.testing.assert_array_equal(out[1], -np.arange(11.0))
         np.testing.assert_array_equal(t, [11.0, 5.0])
         assert ok_cover
+
+
+def test_batch_shard_ranges_tile_the_batch():
+    sys.path.insert(0, os.path.join(ROOT, "osqp-python_b200"))
+    from b200qp import batchbench
+    for batch in (1, 7, 8, 8191, 8192):
+        for world in (1, 2, 3, 4, 8):
+            edges = [batchbench.shard_range(batch, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == batch
+            assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(sizes) <= 1
 
 
 def test_reference_arm_is_rank0_only(monkeypatch, capsys):
