@@ -16,8 +16,8 @@
 //   * CTAs pull QP indices from a global counter, so QPs that need 25 and 200 iterations balance out.
 // Two inner solvers (template flag DENSE):
 //   * DENSE = false: the engine's Jacobi-PCG, as in admm_kernel.cuh (any n, m whose vectors fit shared memory);
-//   * DENSE = true : small QPs (n <= ~150).  K is formed and inverted IN SHARED MEMORY once per rho value
-//     (in-place Gauss-Jordan; K is SPD so no pivoting, a non-positive pivot = NON_CVX) and the PCG is replaced by
+//   * DENSE = true : small QPs (n <= 128).  K is formed in shared memory and inverted IN REGISTERS once per rho
+//     value (Gauss-Jordan; K is SPD so no pivoting, a non-positive pivot = NON_CVX) and the PCG is replaced by
 //     one dense mat-vec d = K^-1 r per ADMM iteration -- 3 CTA barriers per iteration instead of ~30.  The
 //     residual-correction form keeps the step exact to the accuracy of K^-1 relative to the correction d, not x.
 //     This is the reference's "factor once, solve every iteration" scheme (src/osqppurepy/_osqp.py:281-312,
@@ -124,8 +124,115 @@ inline int batch_npad(int n) { return (n + 31) & ~31; }
 inline size_t batch_smem_bytes(int n, int m, bool dense) {
   const int nt = dense ? NTB_DENSE : NTB_PCG;
   size_t d = (size_t)8 * n + (size_t)8 * m + KMAX * (nt / 32) + KMAX;
-  if (dense) d += (size_t)n * batch_ldk(n) + 2 * (size_t)n + (size_t)(nt / batch_npad(n)) * batch_npad(n);
+  if (dense) d += (size_t)n * batch_ldk(n) + 4 * 128 + (size_t)(nt / batch_npad(n)) * batch_npad(n);
   return d * sizeof(double);
+}
+
+// ---- dense mode: K = P + sigma I + A' rho A formed in shared memory (thread j owns row j: no atomics), then
+// inverted by Gauss-Jordan elimination without pivoting (K is SPD; a non-positive pivot means it is not) with
+// the whole matrix held in REGISTERS: thread (ty, tx) = (tid / 16, tid % 16) owns rows ty + 32 a (a < 4) and
+// columns tx + 16 b (b < 8) of a 128 x 128 frame, so one elimination step is 32 FMAs per thread on registers
+// plus 12 broadcast reads of the pivot row / column from a double-buffered shared-memory line (one barrier per
+// step).  Row k and column k of the step are then overwritten with their exact values.  Returns 0 if a pivot
+// was not positive.  Requires n <= 128 and NT == 512.
+constexpr int DENSE_NMAX = 128;
+template <int NT>
+__device__ __noinline__ int dense_build_inverse(const CsrMat P, const CsrMat A, const CsrMat At, const double* rho_v,
+                                                double sigma, int n, int LDK, double* Kinv, double* line) {
+  static_assert(NT == 512, "register tiling assumes 32 x 16 threads");
+  const int tid = threadIdx.x;
+  for (int e = tid; e < n * LDK; e += NT) Kinv[e] = 0.0;
+  __syncthreads();
+  if (tid < n) {
+    double* Kj = Kinv + tid * LDK;
+    for (int k = __ldg(P.ptr + tid); k < __ldg(P.ptr + tid + 1); ++k) Kj[__ldg(P.idx + k)] += __ldg(P.val + k);
+    Kj[tid] += sigma;
+    for (int t = __ldg(At.ptr + tid); t < __ldg(At.ptr + tid + 1); ++t) {
+      const int i = __ldg(At.idx + t);
+      const double f = rho_v[i] * __ldg(At.val + t);
+      for (int k = __ldg(A.ptr + i); k < __ldg(A.ptr + i + 1); ++k) {
+        const int c = __ldg(A.idx + k);
+        Kj[c] = fma(f, __ldg(A.val + k), Kj[c]);
+      }
+    }
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  double T[4][8];
+#pragma unroll
+  for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb) {
+      const int i = ty + 32 * aa, j = tx + 16 * bb;
+      T[aa][bb] = (i < n && j < n) ? Kinv[i * LDK + j] : 0.0;
+    }
+  // line: [2][2][DENSE_NMAX] = {buffer}{row, column}
+  auto publish = [&](int k) {
+    double* rb = line + (k & 1) * 2 * DENSE_NMAX;
+    double* cb = rb + DENSE_NMAX;
+    if (ty == (k & 31)) {
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa)
+        if (aa == (k >> 5)) {
+#pragma unroll
+          for (int bb = 0; bb < 8; ++bb) rb[tx + 16 * bb] = T[aa][bb];
+        }
+    }
+    if (tx == (k & 15)) {
+#pragma unroll
+      for (int bb = 0; bb < 8; ++bb)
+        if (bb == (k >> 4)) {
+#pragma unroll
+          for (int aa = 0; aa < 4; ++aa) cb[ty + 32 * aa] = T[aa][bb];
+        }
+    }
+  };
+  publish(0);
+  __syncthreads();
+  int ok = 1;
+  for (int k = 0; k < n; ++k) {
+    const double* rb = line + (k & 1) * 2 * DENSE_NMAX;
+    const double* cb = rb + DENSE_NMAX;
+    const double akk = rb[k];
+    if (!(akk > 0.0)) ok = 0;
+    const double piv = 1.0 / akk;
+    double rj[8], ci[4];
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb) rj[bb] = rb[tx + 16 * bb] * piv;
+#pragma unroll
+    for (int aa = 0; aa < 4; ++aa) ci[aa] = cb[ty + 32 * aa];
+#pragma unroll
+    for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+      for (int bb = 0; bb < 8; ++bb) T[aa][bb] = fma(-ci[aa], rj[bb], T[aa][bb]);
+    if (ty == (k & 31)) {            // row k: a_kj / a_kk
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa)
+        if (aa == (k >> 5)) {
+#pragma unroll
+          for (int bb = 0; bb < 8; ++bb) T[aa][bb] = rj[bb];
+        }
+    }
+    if (tx == (k & 15)) {            // column k: -a_ik / a_kk, and 1 / a_kk on the diagonal
+#pragma unroll
+      for (int bb = 0; bb < 8; ++bb)
+        if (bb == (k >> 4)) {
+#pragma unroll
+          for (int aa = 0; aa < 4; ++aa) T[aa][bb] = (ty + 32 * aa == k) ? piv : -ci[aa] * piv;
+        }
+    }
+    if (k + 1 < n) publish(k + 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb) {
+      const int i = ty + 32 * aa, j = tx + 16 * bb;
+      if (i < n && j < n) Kinv[i * LDK + j] = T[aa][bb];
+    }
+  __syncthreads();
+  return ok;
 }
 
 template <int LGN, int LGM, int NTB, bool DENSE>
@@ -152,12 +259,11 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
   double* const rho_v = w + m;
   double* const s_red = rho_v + m;
   double* const s_tot = s_red + KMAX * NWB;
-  // dense mode: K^-1 (n x LDK), pivot row / column of the elimination step, partial sums of the mat-vec
+  // dense mode: K^-1 (n x LDK), pivot lines of the elimination, partial sums of the mat-vec
   const int LDK = n | 1, npad = (n + 31) & ~31, PARTS = DENSE ? NTB / npad : 1;
   double* const Kinv = s_tot + KMAX;
-  double* const rowk = Kinv + (DENSE ? n * LDK : 0);
-  double* const colk = rowk + (DENSE ? n : 0);
-  double* const partbuf = colk + (DENSE ? n : 0);
+  double* const rowk = Kinv + (DENSE ? n * LDK : 0);          // [2][2][128] pivot row / column lines of the elimination
+  double* const partbuf = rowk + (DENSE ? 4 * DENSE_NMAX : 0);
   const int tj = tid % npad, ti0 = tid / npad;
 
   constexpr int NGN = NTB / LGN, NGM = NTB / LGM;
@@ -234,47 +340,14 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
     double t_prim = 0, t_ax = 0, t_z = 0;
     double ndx = 0, qdx = 0;
     double rz = 0, r0max = 0;
-    bool time_up = false;
+    bool time_up = false, chk_next = false, adp_next = false;
+    int cnt_chk = 0, cnt_adp = 0;
 
     // ---- dense mode: K = P + sigma I + A' rho A formed row by row (thread j owns row j: no atomics), inverted
     // in place by Gauss-Jordan elimination without pivoting (K is SPD; a non-positive pivot means it is not)
     auto build_inverse = [&]() -> bool {
-      for (int e = tid; e < n * LDK; e += NTB) Kinv[e] = 0.0;
-      __syncthreads();
-      if (tid < n) {
-        double* Kj = Kinv + tid * LDK;
-        for (int k = __ldg(a.P.ptr + tid); k < __ldg(a.P.ptr + tid + 1); ++k) Kj[__ldg(a.P.idx + k)] += __ldg(a.P.val + k);
-        Kj[tid] += sigma;
-        for (int t = __ldg(a.At.ptr + tid); t < __ldg(a.At.ptr + tid + 1); ++t) {
-          const int i = __ldg(a.At.idx + t);
-          const double f = rho_v[i] * __ldg(a.At.val + t);
-          for (int k = __ldg(a.A.ptr + i); k < __ldg(a.A.ptr + i + 1); ++k) {
-            const int c = __ldg(a.A.idx + k);
-            Kj[c] = fma(f, __ldg(a.A.val + k), Kj[c]);
-          }
-        }
-      }
-      __syncthreads();
-      bool ok = true;
-      for (int k = 0; k < n; ++k) {
-        const double akk = Kinv[k * LDK + k];
-        ok = ok && (akk > 0.0);
-        const double piv = 1.0 / akk;
-        if (ti0 == 0 && tj < n) { rowk[tj] = Kinv[k * LDK + tj] * piv; colk[tj] = Kinv[tj * LDK + k]; }
-        __syncthreads();
-        if (tj < n && ti0 < PARTS) {
-          const double rj = rowk[tj];
-          for (int i = ti0; i < n; i += PARTS) {
-            double v;
-            if (i == k) v = (tj == k) ? piv : rj;
-            else if (tj == k) v = -colk[i] * piv;
-            else v = fma(-colk[i], rj, Kinv[i * LDK + tj]);
-            Kinv[i * LDK + tj] = v;
-          }
-        }
-        __syncthreads();
-      }
-      return ok;
+      if constexpr (DENSE) return dense_build_inverse<NTB>(a.P, a.A, a.At, rho_v, sigma, n, LDK, Kinv, rowk) != 0;
+      else return true;
     };
     // d = K^-1 r  (K^-1 symmetric: thread (part, j) walks column j = row j with unit-stride lanes)
     auto dense_apply = [&]() {
@@ -352,6 +425,11 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
           }
         }
       }
+      if (DENSE && !full) {          // the mat-vec needs neither <r, p> nor |r|inf: no reduction on plain iterations
+        __syncthreads();
+        r0max = 1.0;
+        return;
+      }
       if (full && tid == 0) v[BR_TL] = ((double)(global_timer_ns() - t_start) > a.time_limit_ns) ? 1.0 : 0.0;
       cta_reduce<BR_K, NWB>(v, BR_MAXMASK, s_red, s_tot);
       rz = s_tot[BR_RZ];
@@ -413,8 +491,7 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
     // ================================================================ main loop
     for (; status == 0;) {
       const bool last = (k >= a.max_iter);
-      const bool chk = k > 0 && ((a.check_term > 0 && (k % a.check_term) == 0) || last);
-      const bool adp = k > 0 && !last && a.adaptive_rho && a.adapt_interval > 0 && (k % a.adapt_interval) == 0;
+      const bool chk = chk_next, adp = adp_next;     // cadence of iteration k, counted in the previous Z phase
       const bool full = chk || adp;
 
       phase_R(full, false);
@@ -508,10 +585,15 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
       }
 
       // -------------------------------------------------------------- Z phase
+      // check every check_term-th, adapt every adapt_interval-th iteration (counters: no integer division per iteration)
       const int kn = k + 1;
       const bool last_n = (kn >= a.max_iter);
-      const bool full_n = ((a.check_term > 0 && (kn % a.check_term) == 0) || last_n) ||
-                          (!last_n && a.adaptive_rho && a.adapt_interval > 0 && (kn % a.adapt_interval) == 0);
+      bool hit_chk = false, hit_adp = false;
+      if (++cnt_chk == a.check_term) { cnt_chk = 0; hit_chk = true; }
+      if (++cnt_adp == a.adapt_interval) { cnt_adp = 0; hit_adp = true; }
+      chk_next = hit_chk || last_n;
+      adp_next = !last_n && a.adaptive_rho && hit_adp;
+      const bool full_n = chk_next || adp_next;
       {
         double v[BZ_K];
 #pragma unroll

@@ -208,7 +208,7 @@ b200qp_int b200qp_batch_setup(b200qp_batch** batchp, b200qp_int batch, const b20
     BCK(cudaGetDeviceProperties(&prop, b->device));
     // inner solver: K^-1 on chip when it fits next to the vectors (small QPs), else the engine's PCG.
     // B200QP_BATCH_DENSE=0 / 1 forces the choice (1 still requires that it fits).
-    b->dense = batch_smem_bytes(n, m, true) <= (size_t)prop.sharedMemPerBlockOptin;
+    b->dense = n <= DENSE_NMAX && batch_smem_bytes(n, m, true) <= (size_t)prop.sharedMemPerBlockOptin;
     if (const char* e = std::getenv("B200QP_BATCH_DENSE")) b->dense = b->dense && std::atoi(e) != 0;
     b->smem = batch_smem_bytes(n, m, b->dense);
     b->nt = b->dense ? NTB_DENSE : NTB_PCG;
