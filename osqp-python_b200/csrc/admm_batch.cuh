@@ -137,9 +137,15 @@ inline size_t batch_smem_bytes(int n, int m, bool dense) {
 // was not positive.  Requires n <= 128 and NT == 512.
 constexpr int DENSE_NMAX = 128;
 template <int NT>
-__device__ __noinline__ int dense_build_inverse(const CsrMat P, const CsrMat A, const CsrMat At, const double* rho_v,
-                                                double sigma, int n, int LDK, double* Kinv, double* line) {
+__device__ __noinline__ int dense_build_inverse(const CsrMat P, const CsrMat A, const CsrMat At, int off_rho, double sigma,
+                                                int n, int LDK, int off_K, int off_line) {
   static_assert(NT == 512, "register tiling assumes 32 x 16 threads");
+  // offsets into the kernel's dynamic shared memory, not pointers: a pointer argument of a non-inlined function
+  // is generic and every access would go through the L1TEX generic path instead of LDS / STS
+  extern __shared__ double sm_dense[];
+  const double* rho_v = sm_dense + off_rho;
+  double* Kinv = sm_dense + off_K;
+  double* line = sm_dense + off_line;
   const int tid = threadIdx.x;
   for (int e = tid; e < n * LDK; e += NT) Kinv[e] = 0.0;
   __syncthreads();
@@ -346,7 +352,7 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
     // ---- dense mode: K = P + sigma I + A' rho A formed row by row (thread j owns row j: no atomics), inverted
     // in place by Gauss-Jordan elimination without pivoting (K is SPD; a non-positive pivot means it is not)
     auto build_inverse = [&]() -> bool {
-      if constexpr (DENSE) return dense_build_inverse<NTB>(a.P, a.A, a.At, rho_v, sigma, n, LDK, Kinv, rowk) != 0;
+      if constexpr (DENSE) return dense_build_inverse<NTB>(a.P, a.A, a.At, (int)(rho_v - sm), sigma, n, LDK, (int)(Kinv - sm), (int)(rowk - sm)) != 0;
       else return true;
     };
     // d = K^-1 r  (K^-1 symmetric: thread (part, j) walks column j = row j with unit-stride lanes)
