@@ -128,6 +128,51 @@ inline size_t batch_smem_bytes(int n, int m, bool dense) {
   return d * sizeof(double);
 }
 
+constexpr int DENSE_NMAX = 128;
+// 16 Gauss-Jordan steps k = 32 AS + 16 (BS & 1) + 0..15 on the register tile (see dense_build_inverse)
+template <int AS, int BS>
+__device__ __forceinline__ void gj_steps16(double (&T)[4][8], double* line, int ty, int tx, int n, int& ok) {
+  constexpr int K0 = 32 * AS + 16 * (BS & 1);
+  static_assert(BS / 2 == AS, "pivot row block and pivot column block must describe the same k range");
+#pragma unroll 1
+  for (int kk = 0; kk < 16; ++kk) {
+    const int k = K0 + kk;
+    if (k >= n) break;                               // uniform over the CTA
+    double* rb = line + (k & 1) * 2 * DENSE_NMAX;    // double-buffered: one barrier per step
+    double* cb = rb + DENSE_NMAX;
+    const bool own_row = ty == (k & 31), own_col = tx == (k & 15);
+    if (own_row) {
+#pragma unroll
+      for (int bb = 0; bb < 8; ++bb) rb[tx + 16 * bb] = T[AS][bb];
+    }
+    if (own_col) {
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa) cb[ty + 32 * aa] = T[aa][BS];
+    }
+    __syncthreads();
+    const double akk = rb[k];
+    if (!(akk > 0.0)) ok = 0;
+    const double piv = 1.0 / akk;
+    double rj[8], ci[4];
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb) rj[bb] = rb[tx + 16 * bb] * piv;
+#pragma unroll
+    for (int aa = 0; aa < 4; ++aa) ci[aa] = cb[ty + 32 * aa];
+#pragma unroll
+    for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+      for (int bb = 0; bb < 8; ++bb) T[aa][bb] = fma(-ci[aa], rj[bb], T[aa][bb]);
+    if (own_row) {                                   // row k: a_kj / a_kk
+#pragma unroll
+      for (int bb = 0; bb < 8; ++bb) T[AS][bb] = rj[bb];
+    }
+    if (own_col) {                                   // column k: -a_ik / a_kk, and 1 / a_kk on the diagonal
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa) T[aa][BS] = (aa == AS && own_row) ? piv : -ci[aa] * piv;
+    }
+  }
+}
+
 // ---- dense mode: K = P + sigma I + A' rho A formed in shared memory (thread j owns row j: no atomics), then
 // inverted by Gauss-Jordan elimination without pivoting (K is SPD; a non-positive pivot means it is not) with
 // the whole matrix held in REGISTERS: thread (ty, tx) = (tid / 16, tid % 16) owns rows ty + 32 a (a < 4) and
@@ -135,7 +180,6 @@ inline size_t batch_smem_bytes(int n, int m, bool dense) {
 // plus 12 broadcast reads of the pivot row / column from a double-buffered shared-memory line (one barrier per
 // step).  Row k and column k of the step are then overwritten with their exact values.  Returns 0 if a pivot
 // was not positive.  Requires n <= 128 and NT == 512.
-constexpr int DENSE_NMAX = 128;
 template <int NT>
 __device__ __noinline__ int dense_build_inverse(const CsrMat P, const CsrMat A, const CsrMat At, int off_rho, double sigma,
                                                 int n, int LDK, int off_K, int off_line) {
@@ -172,64 +216,19 @@ __device__ __noinline__ int dense_build_inverse(const CsrMat P, const CsrMat A, 
       const int i = ty + 32 * aa, j = tx + 16 * bb;
       T[aa][bb] = (i < n && j < n) ? Kinv[i * LDK + j] : 0.0;
     }
-  // line: [2][2][DENSE_NMAX] = {buffer}{row, column}
-  auto publish = [&](int k) {
-    double* rb = line + (k & 1) * 2 * DENSE_NMAX;
-    double* cb = rb + DENSE_NMAX;
-    if (ty == (k & 31)) {
-#pragma unroll
-      for (int aa = 0; aa < 4; ++aa)
-        if (aa == (k >> 5)) {
-#pragma unroll
-          for (int bb = 0; bb < 8; ++bb) rb[tx + 16 * bb] = T[aa][bb];
-        }
-    }
-    if (tx == (k & 15)) {
-#pragma unroll
-      for (int bb = 0; bb < 8; ++bb)
-        if (bb == (k >> 4)) {
-#pragma unroll
-          for (int aa = 0; aa < 4; ++aa) cb[ty + 32 * aa] = T[aa][bb];
-        }
-    }
-  };
-  publish(0);
-  __syncthreads();
+  // line: [2][2][DENSE_NMAX] = {buffer}{row, column}.  The 128 steps run as 8 blocks of 16 in which the register
+  // index of pivot row (AS) and pivot column (BS) is a compile-time constant: a run-time T[k >> 5][..] would
+  // push the whole tile into local memory.
   int ok = 1;
-  for (int k = 0; k < n; ++k) {
-    const double* rb = line + (k & 1) * 2 * DENSE_NMAX;
-    const double* cb = rb + DENSE_NMAX;
-    const double akk = rb[k];
-    if (!(akk > 0.0)) ok = 0;
-    const double piv = 1.0 / akk;
-    double rj[8], ci[4];
-#pragma unroll
-    for (int bb = 0; bb < 8; ++bb) rj[bb] = rb[tx + 16 * bb] * piv;
-#pragma unroll
-    for (int aa = 0; aa < 4; ++aa) ci[aa] = cb[ty + 32 * aa];
-#pragma unroll
-    for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-      for (int bb = 0; bb < 8; ++bb) T[aa][bb] = fma(-ci[aa], rj[bb], T[aa][bb]);
-    if (ty == (k & 31)) {            // row k: a_kj / a_kk
-#pragma unroll
-      for (int aa = 0; aa < 4; ++aa)
-        if (aa == (k >> 5)) {
-#pragma unroll
-          for (int bb = 0; bb < 8; ++bb) T[aa][bb] = rj[bb];
-        }
-    }
-    if (tx == (k & 15)) {            // column k: -a_ik / a_kk, and 1 / a_kk on the diagonal
-#pragma unroll
-      for (int bb = 0; bb < 8; ++bb)
-        if (bb == (k >> 4)) {
-#pragma unroll
-          for (int aa = 0; aa < 4; ++aa) T[aa][bb] = (ty + 32 * aa == k) ? piv : -ci[aa] * piv;
-        }
-    }
-    if (k + 1 < n) publish(k + 1);
-    __syncthreads();
-  }
+  gj_steps16<0, 0>(T, line, ty, tx, n, ok);
+  gj_steps16<0, 1>(T, line, ty, tx, n, ok);
+  gj_steps16<1, 2>(T, line, ty, tx, n, ok);
+  gj_steps16<1, 3>(T, line, ty, tx, n, ok);
+  gj_steps16<2, 4>(T, line, ty, tx, n, ok);
+  gj_steps16<2, 5>(T, line, ty, tx, n, ok);
+  gj_steps16<3, 6>(T, line, ty, tx, n, ok);
+  gj_steps16<3, 7>(T, line, ty, tx, n, ok);
+  __syncthreads();
 #pragma unroll
   for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
