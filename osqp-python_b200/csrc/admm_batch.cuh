@@ -28,7 +28,7 @@
 namespace b200qp {
 
 constexpr int NTB_PCG = 256;    // threads per CTA, PCG mode (4 CTAs per SM)
-constexpr int NTB_DENSE = 512;  // threads per CTA, dense mode (1 CTA per SM: K^-1 takes most of the shared memory)
+constexpr int NTB_DENSE = 1024; // threads per CTA, dense mode (1 CTA per SM: K^-1 takes most of the shared memory); 512 also built
 
 struct BInfo {                  // per QP, written at exit (64 bytes)
   int status, iter, rho_updates, cg_iters;
@@ -121,69 +121,77 @@ constexpr unsigned BZ_MAXMASK = (1u << BZ_SPRIM) | (1u << BZ_SAX) | (1u << BZ_SZ
 
 inline int batch_ldk(int n) { return n | 1; }                    // odd row stride of K^-1: column reads conflict-free
 inline int batch_npad(int n) { return (n + 31) & ~31; }
-inline size_t batch_smem_bytes(int n, int m, bool dense) {
-  const int nt = dense ? NTB_DENSE : NTB_PCG;
+inline size_t batch_smem_bytes(int n, int m, bool dense, int nt) {
   size_t d = (size_t)8 * n + (size_t)8 * m + KMAX * (nt / 32) + KMAX;
   if (dense) d += (size_t)n * batch_ldk(n) + 4 * 128 + (size_t)(nt / batch_npad(n)) * batch_npad(n);
   return d * sizeof(double);
 }
 
 constexpr int DENSE_NMAX = 128;
-// 16 Gauss-Jordan steps k = 32 AS + 16 (BS & 1) + 0..15 on the register tile (see dense_build_inverse)
-template <int AS, int BS>
-__device__ __forceinline__ void gj_steps16(double (&T)[4][8], double* line, int ty, int tx, int n, int& ok) {
-  constexpr int K0 = 32 * AS + 16 * (BS & 1);
-  static_assert(BS / 2 == AS, "pivot row block and pivot column block must describe the same k range");
+// One block of Gauss-Jordan steps on the register tile (see dense_build_inverse).  Thread (ty, tx) = (tid / TXW,
+// tid % TXW), TXW = NT / 32, owns rows ty + 32 a (a < 4) and columns tx + TXW b (b < 128 / TXW).  Block BLK covers the
+// TXW steps k = TXW BLK + 0 .. TXW - 1, for which the register index of the pivot row (AS) and of the pivot column
+// (BLK) is a compile-time constant -- a run-time T[k >> 5][..] would push the whole tile into local memory.
+template <int NT, int BLK>
+__device__ __forceinline__ void gj_block(double (&T)[4][4096 / NT], double* line, int ty, int tx, int n, int& ok) {
+  constexpr int TXW = NT / 32, NB = 4096 / NT;
+  constexpr int K0 = TXW * BLK, AS = K0 >> 5;
 #pragma unroll 1
-  for (int kk = 0; kk < 16; ++kk) {
+  for (int kk = 0; kk < TXW; ++kk) {
     const int k = K0 + kk;
     if (k >= n) break;                               // uniform over the CTA
     double* rb = line + (k & 1) * 2 * DENSE_NMAX;    // double-buffered: one barrier per step
     double* cb = rb + DENSE_NMAX;
-    const bool own_row = ty == (k & 31), own_col = tx == (k & 15);
+    const bool own_row = ty == (k & 31), own_col = tx == kk;
     if (own_row) {
 #pragma unroll
-      for (int bb = 0; bb < 8; ++bb) rb[tx + 16 * bb] = T[AS][bb];
+      for (int bb = 0; bb < NB; ++bb) rb[tx + TXW * bb] = T[AS][bb];
     }
     if (own_col) {
 #pragma unroll
-      for (int aa = 0; aa < 4; ++aa) cb[ty + 32 * aa] = T[aa][BS];
+      for (int aa = 0; aa < 4; ++aa) cb[ty + 32 * aa] = T[aa][BLK];
     }
     __syncthreads();
     const double akk = rb[k];
     if (!(akk > 0.0)) ok = 0;
     const double piv = 1.0 / akk;
-    double rj[8], ci[4];
+    double rj[NB], ci[4];
 #pragma unroll
-    for (int bb = 0; bb < 8; ++bb) rj[bb] = rb[tx + 16 * bb] * piv;
+    for (int bb = 0; bb < NB; ++bb) rj[bb] = rb[tx + TXW * bb] * piv;
 #pragma unroll
     for (int aa = 0; aa < 4; ++aa) ci[aa] = cb[ty + 32 * aa];
 #pragma unroll
     for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
-      for (int bb = 0; bb < 8; ++bb) T[aa][bb] = fma(-ci[aa], rj[bb], T[aa][bb]);
+      for (int bb = 0; bb < NB; ++bb) T[aa][bb] = fma(-ci[aa], rj[bb], T[aa][bb]);
     if (own_row) {                                   // row k: a_kj / a_kk
 #pragma unroll
-      for (int bb = 0; bb < 8; ++bb) T[AS][bb] = rj[bb];
+      for (int bb = 0; bb < NB; ++bb) T[AS][bb] = rj[bb];
     }
     if (own_col) {                                   // column k: -a_ik / a_kk, and 1 / a_kk on the diagonal
 #pragma unroll
-      for (int aa = 0; aa < 4; ++aa) T[aa][BS] = (aa == AS && own_row) ? piv : -ci[aa] * piv;
+      for (int aa = 0; aa < 4; ++aa) T[aa][BLK] = (aa == AS && own_row) ? piv : -ci[aa] * piv;
     }
   }
+}
+template <int NT, int BLK>
+__device__ __forceinline__ void gj_blocks(double (&T)[4][4096 / NT], double* line, int ty, int tx, int n, int& ok) {
+  gj_block<NT, BLK>(T, line, ty, tx, n, ok);
+  if constexpr (BLK + 1 < 4096 / NT) gj_blocks<NT, BLK + 1>(T, line, ty, tx, n, ok);
 }
 
 // ---- dense mode: K = P + sigma I + A' rho A formed in shared memory (thread j owns row j: no atomics), then
 // inverted by Gauss-Jordan elimination without pivoting (K is SPD; a non-positive pivot means it is not) with
-// the whole matrix held in REGISTERS: thread (ty, tx) = (tid / 16, tid % 16) owns rows ty + 32 a (a < 4) and
-// columns tx + 16 b (b < 8) of a 128 x 128 frame, so one elimination step is 32 FMAs per thread on registers
-// plus 12 broadcast reads of the pivot row / column from a double-buffered shared-memory line (one barrier per
-// step).  Row k and column k of the step are then overwritten with their exact values.  Returns 0 if a pivot
-// was not positive.  Requires n <= 128 and NT == 512.
+// the whole matrix held in REGISTERS: with TXW = NT / 32, thread (ty, tx) = (tid / TXW, tid % TXW) owns rows
+// ty + 32 a (a < 4) and columns tx + TXW b (b < 128 / TXW) of a 128 x 128 frame, so one elimination step is 4096 / NT
+// FMAs per thread on registers plus a few broadcast reads of the pivot row / column from a double-buffered
+// shared-memory line (one barrier per step).  Row k and column k of the step are then overwritten with their
+// exact values.  Returns 0 if a pivot was not positive.  Requires n <= 128 and NT = 512 or 1024.
 template <int NT>
 __device__ __noinline__ int dense_build_inverse(const CsrMat P, const CsrMat A, const CsrMat At, int off_rho, double sigma,
                                                 int n, int LDK, int off_K, int off_line) {
-  static_assert(NT == 512, "register tiling assumes 32 x 16 threads");
+  static_assert(NT == 512 || NT == 1024, "register tiling assumes 32 x 16 or 32 x 32 threads");
+  constexpr int TXW = NT / 32, NB = 4096 / NT;
   // offsets into the kernel's dynamic shared memory, not pointers: a pointer argument of a non-inlined function
   // is generic and every access would go through the L1TEX generic path instead of LDS / STS
   extern __shared__ double sm_dense[];
@@ -207,33 +215,24 @@ __device__ __noinline__ int dense_build_inverse(const CsrMat P, const CsrMat A, 
     }
   }
   __syncthreads();
-  const int ty = tid >> 4, tx = tid & 15;
-  double T[4][8];
+  const int ty = tid / TXW, tx = tid % TXW;
+  double T[4][NB];
 #pragma unroll
   for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
-    for (int bb = 0; bb < 8; ++bb) {
-      const int i = ty + 32 * aa, j = tx + 16 * bb;
+    for (int bb = 0; bb < NB; ++bb) {
+      const int i = ty + 32 * aa, j = tx + TXW * bb;
       T[aa][bb] = (i < n && j < n) ? Kinv[i * LDK + j] : 0.0;
     }
-  // line: [2][2][DENSE_NMAX] = {buffer}{row, column}.  The 128 steps run as 8 blocks of 16 in which the register
-  // index of pivot row (AS) and pivot column (BS) is a compile-time constant: a run-time T[k >> 5][..] would
-  // push the whole tile into local memory.
+  // line: [2][2][DENSE_NMAX] = {buffer}{row, column}
   int ok = 1;
-  gj_steps16<0, 0>(T, line, ty, tx, n, ok);
-  gj_steps16<0, 1>(T, line, ty, tx, n, ok);
-  gj_steps16<1, 2>(T, line, ty, tx, n, ok);
-  gj_steps16<1, 3>(T, line, ty, tx, n, ok);
-  gj_steps16<2, 4>(T, line, ty, tx, n, ok);
-  gj_steps16<2, 5>(T, line, ty, tx, n, ok);
-  gj_steps16<3, 6>(T, line, ty, tx, n, ok);
-  gj_steps16<3, 7>(T, line, ty, tx, n, ok);
+  gj_blocks<NT, 0>(T, line, ty, tx, n, ok);
   __syncthreads();
 #pragma unroll
   for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
-    for (int bb = 0; bb < 8; ++bb) {
-      const int i = ty + 32 * aa, j = tx + 16 * bb;
+    for (int bb = 0; bb < NB; ++bb) {
+      const int i = ty + 32 * aa, j = tx + TXW * bb;
       if (i < n && j < n) Kinv[i * LDK + j] = T[aa][bb];
     }
   __syncthreads();

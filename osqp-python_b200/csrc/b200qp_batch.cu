@@ -64,12 +64,18 @@ __global__ void kb_spmv(CsrMat A, int batch, const double* __restrict__ xs, doub
 
 typedef void (*batch_fn)(const BArgs);
 int pick_blg(double avg) { return avg <= 12.0 ? 4 : 16; }
-batch_fn pick_batch_kernel(int lgn, int lgm, bool dense) {
+batch_fn pick_batch_kernel(int lgn, int lgm, bool dense, int nt) {
+  if (dense && nt == 512) {
+    if (lgn == 4 && lgm == 4) return admm_batch_kernel<4, 4, 512, true>;
+    if (lgn == 4 && lgm == 16) return admm_batch_kernel<4, 16, 512, true>;
+    if (lgn == 16 && lgm == 4) return admm_batch_kernel<16, 4, 512, true>;
+    return admm_batch_kernel<16, 16, 512, true>;
+  }
   if (dense) {
-    if (lgn == 4 && lgm == 4) return admm_batch_kernel<4, 4, NTB_DENSE, true>;
-    if (lgn == 4 && lgm == 16) return admm_batch_kernel<4, 16, NTB_DENSE, true>;
-    if (lgn == 16 && lgm == 4) return admm_batch_kernel<16, 4, NTB_DENSE, true>;
-    return admm_batch_kernel<16, 16, NTB_DENSE, true>;
+    if (lgn == 4 && lgm == 4) return admm_batch_kernel<4, 4, 1024, true>;
+    if (lgn == 4 && lgm == 16) return admm_batch_kernel<4, 16, 1024, true>;
+    if (lgn == 16 && lgm == 4) return admm_batch_kernel<16, 4, 1024, true>;
+    return admm_batch_kernel<16, 16, 1024, true>;
   }
   if (lgn == 4 && lgm == 4) return admm_batch_kernel<4, 4, NTB_PCG, false>;
   if (lgn == 4 && lgm == 16) return admm_batch_kernel<4, 16, NTB_PCG, false>;
@@ -208,17 +214,19 @@ b200qp_int b200qp_batch_setup(b200qp_batch** batchp, b200qp_int batch, const b20
     BCK(cudaGetDeviceProperties(&prop, b->device));
     // inner solver: K^-1 on chip when it fits next to the vectors (small QPs), else the engine's PCG.
     // B200QP_BATCH_DENSE=0 / 1 forces the choice (1 still requires that it fits).
-    b->dense = n <= DENSE_NMAX && batch_smem_bytes(n, m, true) <= (size_t)prop.sharedMemPerBlockOptin;
+    int nt_dense = NTB_DENSE;
+    if (const char* e = std::getenv("B200QP_BATCH_NT")) { const int v = std::atoi(e); if (v == 512 || v == 1024) nt_dense = v; }
+    b->dense = n <= DENSE_NMAX && batch_smem_bytes(n, m, true, nt_dense) <= (size_t)prop.sharedMemPerBlockOptin;
     if (const char* e = std::getenv("B200QP_BATCH_DENSE")) b->dense = b->dense && std::atoi(e) != 0;
-    b->smem = batch_smem_bytes(n, m, b->dense);
-    b->nt = b->dense ? NTB_DENSE : NTB_PCG;
+    b->nt = b->dense ? nt_dense : NTB_PCG;
+    b->smem = batch_smem_bytes(n, m, b->dense, b->nt);
     if (b->smem > (size_t)prop.sharedMemPerBlockOptin) {
       std::fprintf(stderr, "[b200qp] batch: n = %d, m = %d needs %zu bytes of shared memory per QP (limit %zu); "
                            "use one b200qp_solver per QP for problems of this size\n",
                    n, m, b->smem, (size_t)prop.sharedMemPerBlockOptin);
       throw (int)B200QP_MEM_ALLOC_ERROR;
     }
-    batch_fn fn = pick_batch_kernel(b->lgn, b->lgm, b->dense);
+    batch_fn fn = pick_batch_kernel(b->lgn, b->lgm, b->dense, b->nt);
     BCK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     int occ = 0;
     BCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, b->nt, b->smem));
@@ -264,7 +272,7 @@ b200qp_int b200qp_batch_solve(b200qp_batch* b) {
     a.rho_is_vec = st->rho_is_vec; a.check_dualgap = st->check_dualgap;
     a.warm = st->warm_starting ? 1 : 0;
     BCK(cudaMemsetAsync(b->next, 0, sizeof(int), b->stream));
-    batch_fn fn = pick_batch_kernel(b->lgn, b->lgm, b->dense);
+    batch_fn fn = pick_batch_kernel(b->lgn, b->lgm, b->dense, b->nt);
     BCK(cudaEventRecord(b->ev0, b->stream));
     fn<<<b->grid, b->nt, b->smem, b->stream>>>(a);
     BCK(cudaEventRecord(b->ev1, b->stream));

@@ -67,7 +67,7 @@ def test_mpc_batch_dense_matches_direct_oracle_iterations():
     prob.setup(P, q, A, l, u, verbose=False, warm_starting=False)
     res = prob.solve()
     st = prob.stats()
-    assert st["dense"] == 1 and st["block"] == 512 and st["cg_iters"] == 0 and st["kernel_ms"] > 0
+    assert st["dense"] == 1 and st["block"] in (512, 1024) and st["cg_iters"] == 0 and st["kernel_ms"] > 0
     for b in range(B):
         ora = _oracle_element(P, q, A, l[0], u[0], q, l[b], u[b], rho_eq_factor=10.0)
         assert res.info.status[b] == ora.info.status == "solved"
