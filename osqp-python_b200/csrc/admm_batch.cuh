@@ -28,7 +28,8 @@
 namespace b200qp {
 
 constexpr int NTB_PCG = 256;    // threads per CTA, PCG mode (4 CTAs per SM)
-constexpr int NTB_DENSE = 1024; // threads per CTA, dense mode (1 CTA per SM: K^-1 takes most of the shared memory); 512 also built
+constexpr int NTB_DENSE = 512;  // threads per CTA, dense mode (1 CTA per SM: K^-1 takes most of the shared memory); a 1024-thread
+                                // build exists for A/B runs (B200QP_BATCH_NT) and measured 23 % slower on config 5
 
 struct BInfo {                  // per QP, written at exit (64 bytes)
   int status, iter, rho_updates, cg_iters;
@@ -42,6 +43,7 @@ struct BArgs {
   const double *q, *l, *u;                           // [batch][n | m], scaled
   double *xs, *zs, *ys, *rho_b;                      // per-QP ADMM state, scaled space (kept between solves)
   double *sol_x, *sol_y, *cert_n, *cert_m;           // [batch][n | m], unscaled results
+  double *kcache, *rcache;                           // dense mode, per CTA: K^-1 [n * ldk] of the last cold rho vector [m]
   BInfo* info;
   int* next;                                         // work counter
   double sigma, alpha, eps_abs, eps_rel, eps_pinf, eps_dinf, c, adapt_tol, cg_tol_frac, rho_eq_factor, time_limit_ns;
@@ -283,6 +285,7 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
   const double* Einv_t = a.unscale ? a.Einv : nullptr;
   const double* E_t = a.unscale ? a.E : nullptr;
 
+  int have_cache = 0;                      // dense mode: this CTA has stored an inverse in a.kcache
   for (;;) {
     __syncthreads();                       // the previous QP is completely stored
     if (tid == 0) s_qp = atomicAdd(a.next, 1);
@@ -374,7 +377,27 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
       __syncthreads();
     };
     if (DENSE) {
-      if (!build_inverse()) status = 9;
+      // K^-1 depends on the rho vector only.  QPs of one batch usually start from the same one (same constraint
+      // types, rho = settings.rho), so every CTA keeps the first inverse it computes in global memory (L2) and
+      // re-loads it -- 0.1 MB from L2 instead of n Gauss-Jordan steps -- whenever the rho vector matches.
+      double* kc = a.kcache + (size_t)blockIdx.x * n * LDK;
+      double* rc = a.rcache + (size_t)blockIdx.x * m;
+      int same = have_cache;
+      if (have_cache)
+        for (int i = tid; i < m; i += NTB) same = same && (rc[i] == rho_v[i]);
+      same = __syncthreads_and(same);
+      if (same) {
+        for (int e = tid; e < n * LDK; e += NTB) Kinv[e] = kc[e];
+        __syncthreads();
+      } else {
+        if (!build_inverse()) status = 9;
+        if (!have_cache && status == 0) {
+          for (int e = tid; e < n * LDK; e += NTB) kc[e] = Kinv[e];
+          for (int i = tid; i < m; i += NTB) rc[i] = rho_v[i];
+          have_cache = 1;
+          __syncthreads();
+        }
+      }
     }
 
     // R phase: r = -(P x + q) + A' w2, p = Minv r; full = also the dual-side residual quantities;

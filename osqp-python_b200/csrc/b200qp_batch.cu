@@ -95,6 +95,7 @@ struct b200qp_batch {
   double *xs = nullptr, *zs = nullptr, *ys = nullptr, *rho_b = nullptr;
   double *sol_x = nullptr, *sol_y = nullptr, *cert_n = nullptr, *cert_m = nullptr;
   double* stage = nullptr;                                      // batch * max(n, m) doubles
+  double *kcache = nullptr, *rcache = nullptr;                  // dense mode: per-CTA inverse cache
   BInfo* info = nullptr;
   int* next = nullptr;
   // pinned host mirrors of the last solve
@@ -103,12 +104,12 @@ struct b200qp_batch {
   int lgn = 4, lgm = 4, grid = 1, nt = NTB_PCG;
   bool dense = false;
   size_t smem = 0;
-  bool solved = false;
+  bool solved = false, any_cert = false;
   b200qp_batch_stats stats{};
 
   ~b200qp_batch() {
     cudaSetDevice(device);
-    for (double* p : {q, l, u, xs, zs, ys, rho_b, sol_x, sol_y, cert_n, cert_m, stage})
+    for (double* p : {q, l, u, xs, zs, ys, rho_b, sol_x, sol_y, cert_n, cert_m, stage, kcache, rcache})
       if (p) cudaFree(p);
     if (info) cudaFree(info);
     if (next) cudaFree(next);
@@ -232,6 +233,10 @@ b200qp_int b200qp_batch_setup(b200qp_batch** batchp, b200qp_int batch, const b20
     BCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, b->nt, b->smem));
     if (occ < 1) throw (int)B200QP_ALGEBRA_LOAD_ERROR;
     b->grid = std::min(batch, occ * prop.multiProcessorCount);
+    if (b->dense) {
+      b->kcache = dalloc((size_t)b->grid * n * batch_ldk(n));
+      b->rcache = dalloc((size_t)b->grid * std::max(m, 1));
+    }
     b->stats.grid = b->grid; b->stats.block = b->nt; b->stats.smem_bytes = (int)b->smem; b->stats.dense = b->dense ? 1 : 0;
     b->stats.batch = batch; b->stats.n = n; b->stats.m = m;
   } catch (int code) {
@@ -262,6 +267,7 @@ b200qp_int b200qp_batch_solve(b200qp_batch* b) {
     a.xs = b->xs; a.zs = b->zs; a.ys = b->ys; a.rho_b = b->rho_b;
     a.sol_x = b->sol_x; a.sol_y = b->sol_y; a.cert_n = b->cert_n; a.cert_m = b->cert_m;
     a.info = b->info; a.next = b->next;
+    a.kcache = b->kcache; a.rcache = b->rcache;
     a.sigma = st->sigma; a.alpha = st->alpha; a.eps_abs = st->eps_abs; a.eps_rel = st->eps_rel;
     a.eps_pinf = st->eps_prim_inf; a.eps_dinf = st->eps_dual_inf; a.c = b->v.c; a.adapt_tol = st->adaptive_rho_tolerance;
     a.cg_tol_frac = st->cg_tol_fraction; a.rho_eq_factor = b->v.rho_eq_factor; a.time_limit_ns = st->time_limit * 1e9;
@@ -291,13 +297,10 @@ b200qp_int b200qp_batch_solve(b200qp_batch* b) {
       const int s = b->h_info[i].status;
       any_cert = any_cert || (s >= B200QP_PRIMAL_INFEASIBLE && s <= B200QP_DUAL_INFEASIBLE_INACCURATE);
     }
+    b->any_cert = any_cert;
     if (any_cert) {   // certificates are rare: fetch them only when some element is infeasible
       BCK(cudaMemcpy(b->h_cn, b->cert_n, bn * sizeof(double), cudaMemcpyDeviceToHost));
       if (bm) BCK(cudaMemcpy(b->h_cm, b->cert_m, bm * sizeof(double), cudaMemcpyDeviceToHost));
-    } else {
-      const double nanv = std::nan("");
-      std::fill(b->h_cn, b->h_cn + bn, nanv);
-      std::fill(b->h_cm, b->h_cm + bm, nanv);
     }
     b->stats.admm_iters = it; b->stats.cg_iters = cg; b->stats.kernel_ms = ms;
     b->solved = true;
@@ -395,8 +398,9 @@ b200qp_int b200qp_batch_get_solution(const b200qp_batch* b, b200qp_float* x, b20
   const size_t bn = (size_t)b->batch * b->n, bm = (size_t)b->batch * b->m;
   if (x) std::memcpy(x, b->h_x, bn * sizeof(double));
   if (y) std::memcpy(y, b->h_y, bm * sizeof(double));
-  if (prim_inf_cert) std::memcpy(prim_inf_cert, b->h_cm, bm * sizeof(double));
-  if (dual_inf_cert) std::memcpy(dual_inf_cert, b->h_cn, bn * sizeof(double));
+  const double nanv = std::nan("");   // no element was infeasible: all-NaN certificates, as the reference returns
+  if (prim_inf_cert) { if (b->any_cert) std::memcpy(prim_inf_cert, b->h_cm, bm * sizeof(double)); else std::fill(prim_inf_cert, prim_inf_cert + bm, nanv); }
+  if (dual_inf_cert) { if (b->any_cert) std::memcpy(dual_inf_cert, b->h_cn, bn * sizeof(double)); else std::fill(dual_inf_cert, dual_inf_cert + bn, nanv); }
   return 0;
 }
 

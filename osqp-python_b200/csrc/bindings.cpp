@@ -222,8 +222,12 @@ class BatchSolver {
     return status;
   }
   b200qp_int update_rho(b200qp_float rho) { return b200qp_batch_update_rho(b_, rho); }
-  py::dict solution() const {
+  py::dict solution(bool certificates) const {
     py::array_t<b200qp_float> x({(py::ssize_t)batch_, (py::ssize_t)n_}), y({(py::ssize_t)batch_, (py::ssize_t)m_});
+    if (!certificates) {
+      b200qp_batch_get_solution(b_, x.mutable_data(), y.mutable_data(), nullptr, nullptr);
+      return py::dict("x"_a = x, "y"_a = y);
+    }
     py::array_t<b200qp_float> pc({(py::ssize_t)batch_, (py::ssize_t)m_}), dc({(py::ssize_t)batch_, (py::ssize_t)n_});
     b200qp_batch_get_solution(b_, x.mutable_data(), y.mutable_data(), pc.mutable_data(), dc.mutable_data());
     return py::dict("x"_a = x, "y"_a = y, "prim_inf_cert"_a = pc, "dual_inf_cert"_a = dc);
@@ -417,7 +421,7 @@ PYBIND11_MODULE(osqp_cuda, mod) {
       .def("warm_start", &BatchSolver::warm_start, "x"_a.none(true) = py::none(), "y"_a.none(true) = py::none())
       .def("update_settings", &BatchSolver::update_settings)
       .def("update_rho", &BatchSolver::update_rho)
-      .def("get_solution", &BatchSolver::solution)
+      .def("get_solution", &BatchSolver::solution, "certificates"_a = true)
       .def("get_info", &BatchSolver::info)
       .def("get_stats", &BatchSolver::stats);
 

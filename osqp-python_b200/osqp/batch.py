@@ -85,13 +85,15 @@ class OSQPBatch(OSQP):
         if rc:
             raise OSQPException(rc)
         info = self._solver.get_info()
-        sol = self._solver.get_solution()
         sv = info["status_val"]
+        # certificates exist only for infeasible elements: fetch them only then (None otherwise)
+        infeasible = bool(np.any((sv >= SolverStatus.OSQP_PRIMAL_INFEASIBLE) & (sv <= SolverStatus.OSQP_DUAL_INFEASIBLE_INACCURATE)))
+        sol = self._solver.get_solution(certificates=infeasible)
         if raise_error and np.any(sv != SolverStatus.OSQP_SOLVED):
             raise OSQPException(int(sv[sv != SolverStatus.OSQP_SOLVED][0]))
         info["status"] = [_STATUS_TEXT.get(int(s), "unsolved") for s in sv]
-        return SimpleNamespace(x=sol["x"], y=sol["y"], prim_inf_cert=sol["prim_inf_cert"],
-                               dual_inf_cert=sol["dual_inf_cert"], info=SimpleNamespace(**info))
+        return SimpleNamespace(x=sol["x"], y=sol["y"], prim_inf_cert=sol.get("prim_inf_cert"),
+                               dual_inf_cert=sol.get("dual_inf_cert"), info=SimpleNamespace(**info))
 
     def stats(self):
         return self._solver.get_stats()

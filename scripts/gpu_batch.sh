@@ -13,11 +13,14 @@ args = types.SimpleNamespace(steps=int(sys.argv[1]), warmup=3)
 print(json.dumps(batchbench.batch_line(args, with_cpu=len(sys.argv) > 2)))
 PY
 timeout 600 python /tmp/bb.py 10 cpu > gpurun_out/batchbench_${TAG}_dense.json 2> gpurun_out/batchbench_$TAG.err; echo "batchbench dense rc=$?"
-B200QP_BATCH_NT=512 timeout 600 python /tmp/bb.py 10 > gpurun_out/batchbench_${TAG}_dense512.json 2>> gpurun_out/batchbench_$TAG.err; echo "batchbench dense512 rc=$?"
+if [ "${AB:-0}" = "1" ]; then
+B200QP_BATCH_NT=1024 timeout 600 python /tmp/bb.py 10 > gpurun_out/batchbench_${TAG}_dense1024.json 2>> gpurun_out/batchbench_$TAG.err; echo "batchbench dense1024 rc=$?"
 B200QP_BATCH_DENSE=0 timeout 600 python /tmp/bb.py 10 > gpurun_out/batchbench_${TAG}_pcg.json 2>> gpurun_out/batchbench_$TAG.err; echo "batchbench pcg rc=$?"
+fi
 python - <<PY
 import json
-for k in ("dense", "dense512", "pcg"):
+import os
+for k in [k for k in ("dense", "dense1024", "pcg") if os.path.exists("gpurun_out/batchbench_${TAG}_%s.json" % k)]:
     d = json.load(open("gpurun_out/batchbench_${TAG}_%s.json" % k))
     print(k, "QPs/s", round(d["value"]), "e2e", round(d["e2e"]["value"]), "ms", round(d["ms_per_step"], 2), "it/qp", round(d["admm_iters_per_qp"], 1),
           "cg/it", round(d["pcg_iters_per_admm_iter"], 2), "grid", d["grid"], "solved", d["solved_fraction"], d.get("cpu_baseline", {}).get("value"))
