@@ -44,7 +44,7 @@ N_VARS = int(os.environ.get("B200QP_BENCH_N", 1_000_000))
 N_CONS = int(os.environ.get("B200QP_BENCH_M", N_VARS))
 NNZ_ROW = 10
 SEED = 3
-ENGINE_SPEC = dict(cg_max_iter=100, cg_tol_fraction=0.05, rho_eq_factor=10.0)   # the engine's defaults, for the CPU port
+ENGINE_SPEC = dict(cg_max_iter=100, cg_tol_fraction=0.1, rho_eq_factor=10.0)   # the engine's defaults, for the CPU port
 SOLVE_KW = dict(eps_abs=1e-3, eps_rel=1e-3, max_iter=4000, warm_starting=False, polishing=False)
 
 

@@ -99,7 +99,7 @@ class Settings:
     time_limit: float = 1e10
     # indirect mode (engine spec)
     cg_max_iter: int = 100
-    cg_tol_fraction: float = 0.05
+    cg_tol_fraction: float = 0.1
     cg_precond: int = 1
     # rho on equality rows = rho_eq_factor * rho.  Reference constant: 1e3 (ref:27); the engine's
     # PCG-friendly default is 10 -- pass rho_eq_factor=10 to mirror the engine.

@@ -87,7 +87,7 @@ def test_engine_vs_live_oracle(name):
     case = load_case(name)
     kw = dict(max_iter=40000, check_termination=1, adaptive_rho_interval=50)
     res, prob = run_case_engine(case, **kw)
-    ind = run_case_oracle(case, "indirect", cg_max_iter=100, cg_tol_fraction=0.05, rho_eq_factor=10.0, **kw)
+    ind = run_case_oracle(case, "indirect", cg_max_iter=100, cg_tol_fraction=0.1, rho_eq_factor=10.0, **kw)
     dire = run_case_oracle(case, "direct", **kw)
     assert status_name(res) == ind.info.status == dire.info.status == "solved"
     # identical algorithm, different floating-point summation order: short runs agree to a few iterations,
