@@ -45,6 +45,11 @@ N_CONS = int(os.environ.get("B200QP_BENCH_M", N_VARS))
 NNZ_ROW = 10
 SEED = 3
 ENGINE_SPEC = dict(cg_max_iter=100, cg_tol_fraction=0.1, rho_eq_factor=10.0)   # the engine's defaults, for the CPU port
+# dram__bytes_read.sum + dram__bytes_write.sum of one admm_kernel launch of this workload, from the committed
+# `ncu --set full` capture (234.72 GB + 12.15 GB; the n- and m-vectors stay L2-resident, so it is below the
+# algorithmic byte count); only valid for the default problem size
+NCU_TRAFFIC_BYTES = 246.866e9 if (N_VARS, N_CONS) == (1_000_000, 1_000_000) else None
+NCU_TRAFFIC_SOURCE = "profiles/r1c_admm_kernel_ncu_raw.csv (75 ADMM / 642 PCG iterations per launch)"
 SOLVE_KW = dict(eps_abs=1e-3, eps_rel=1e-3, max_iter=4000, warm_starting=False, polishing=False)
 
 
@@ -252,7 +257,8 @@ def run_ours(args):
                    "settings": {k: v for k, v in SOLVE_KW.items()}},
         "roofline": {"bound": "hbm", "kernel": "b200qp::admm_kernel (persistent, one launch per solve)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "frac_of_8TBs": achieved / 8000.0, "peak_source": peak_src, "traffic": None,
+                     "frac_of_8TBs": achieved / 8000.0, "peak_source": peak_src, "traffic": NCU_TRAFFIC_BYTES,
+                     "traffic_source": NCU_TRAFFIC_SOURCE,
                      "algo_bytes_per_launch": bytes_algo / args.steps, "ms_per_launch": dev_ms / args.steps},
         "e2e": {"value": iters / (wall_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n,
                 "d2h_bytes_per_step": 16 * (n + m) + 128, "ms_per_step": wall_ms / args.steps,
