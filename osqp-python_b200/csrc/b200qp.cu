@@ -250,23 +250,30 @@ void refresh_q_norms(b200qp_solver* sv) {
   w->nq_t = h[0];
 }
 
-// balanced contiguous row ranges: weight(row) = nnz of the row in each matrix + a constant
-void make_partition(int rows, int G, const std::vector<const std::vector<int>*>& ptrs, std::vector<int>& part) {
+// balanced contiguous row ranges.  lg == 0: weight(row) = nnz of the row in each matrix + a constant.
+// lg > 0 (the persistent kernel's phases, lg lanes cooperate on a row): a row costs lg lanes x (its trips through
+// the lane loop + a fixed number of trips for the pointer loads, the shuffle reduction and the store) -- with 32
+// lanes a 1-entry row is as expensive as a 32-entry one, and counting it by its nnz left the CTAs that own the
+// short rows of a Lasso / SVM matrix as stragglers (config 2: 1.38 ms per A p instead of 0.3 ms).
+void make_partition(int rows, int G, const std::vector<const std::vector<int>*>& ptrs, std::vector<int>& part, int lg = 0) {
   part.assign(G + 1, rows);
   part[0] = 0;
   if (rows == 0) { std::fill(part.begin(), part.end(), 0); return; }
-  auto wsum = [&](int r) {  // total weight of rows [0, r)
-    long long s = 8LL * r;
-    for (auto* p : ptrs) s += (*p)[r];
-    return s;
-  };
-  const long long total = wsum(rows);
+  std::vector<long long> pre(rows + 1, 0);   // prefix sums of the row weights
+  for (int r = 0; r < rows; ++r) {
+    long long wr = lg > 0 ? 0 : 8;
+    for (auto* p : ptrs) {
+      const long long nz = (*p)[r + 1] - (*p)[r];
+      wr += lg > 0 ? (long long)lg * ((nz + lg - 1) / lg + 3) : nz;
+    }
+    pre[r + 1] = pre[r] + wr;
+  }
+  const long long total = pre[rows];
   int r = 0;
   for (int g = 1; g < G; ++g) {
     const long long target = total * g / G;
-    int lo = r, hi = rows;
-    while (lo < hi) { const int mid = (lo + hi) / 2; if (wsum(mid) < target) lo = mid + 1; else hi = mid; }
-    r = lo;
+    r = (int)(std::lower_bound(pre.begin() + r, pre.end(), target) - pre.begin());
+    r = std::min(r, rows);
     part[g] = r;
   }
   part[G] = rows;
@@ -663,8 +670,8 @@ b200qp_int b200qp_setup(b200qp_solver** solverp, const b200qp_csc* P, const b200
     if (const char* e = std::getenv("B200QP_GRID")) want = std::atoll(e);
     w->G = (int)std::min<long long>(std::max<long long>(want, 1), w->max_coop);
     std::vector<int> pn, pm;
-    make_partition(n, w->G, {&w->P.h_ptr, &w->At.h_ptr}, pn);
-    make_partition(m, w->G, {&w->A.h_ptr}, pm);
+    make_partition(n, w->G, {&w->P.h_ptr, &w->At.h_ptr}, pn, w->lgn);
+    make_partition(m, w->G, {&w->A.h_ptr}, pm, w->lgm);
     w->part_n.alloc(w->G + 1); w->part_n.upload(pn.data(), w->G + 1, s);
     w->part_m.alloc(w->G + 1); w->part_m.upload(pm.data(), w->G + 1, s);
     w->red.alloc((size_t)2 * KMAX * w->G); w->red.zero(s);
@@ -1069,14 +1076,14 @@ b200qp_int b200qp_dist_setup(b200qp_solver** solverp, b200qp_int rank, b200qp_in
     {   // local rows of A_g: weights from the global row pointer, shifted
       std::vector<int> lp(mg + 1);
       for (int i = 0; i <= mg; ++i) lp[i] = w->A.h_ptr[mlo + i] - w->A.h_ptr[mlo];
-      make_partition(mg, d.G, {&lp}, pm);
+      make_partition(mg, d.G, {&lp}, pm, d.lgm);
     }
-    make_partition(n, d.G, {&d.Atg.h_ptr}, pf);
+    make_partition(n, d.G, {&d.Atg.h_ptr}, pf, d.lgn);
     {   // my slice by nnz(P): partition the sub-range, then shift to absolute row numbers
       const int a0 = d.slice[rank], a1 = d.slice[rank + 1];
       std::vector<int> lp(a1 - a0 + 1);
       for (int i = 0; i <= a1 - a0; ++i) lp[i] = w->P.h_ptr[a0 + i] - w->P.h_ptr[a0];
-      make_partition(a1 - a0, d.G, {&lp}, ps);
+      make_partition(a1 - a0, d.G, {&lp}, ps, d.lgn);
       for (int& v : ps) v += a0;
     }
     for (int g = 0; g <= d.G; ++g) pu[g] = (int)((long long)n * g / d.G);
