@@ -15,6 +15,8 @@ One *step* = one complete cold-start solve() of that QP to the default tolerance
   roofline     the dominant (only hot) kernel is the persistent ADMM kernel: algorithmic HBM bytes of
                the launch (byte model in DESIGN.md, computed by the engine from its own iteration
                counters) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+  structured   config 4's sizes with banded column indices (same kernels and byte model): what the engine reaches
+               when the gathers have locality; sub-object with its own roofline and SpMV figures.
   batch        BASELINE configs[4] as a sub-object: 8192 independent MPC QPs sharded over the GPUs (QPs/s,
                device-timed and end to end; b200qp/batchbench.py).
   cpu_baseline the CPU oracle (port of the reference algorithm, engine-spec PCG mode because a direct
@@ -205,6 +207,35 @@ def spmv_line(A, peak):
     return res
 
 
+def structured_line(args, peak):
+    """Config 4's sizes (n = m = 1e6, 10 nnz per row of A) with LOCALITY in the column indices (every index within
+    +-64 of the diagonal position): the same kernels, the same byte model -- shows what the engine reaches when
+    the gathers are not uniformly random (config 4 proper is bound by the L1TEX / L2 gather rate)."""
+    import osqp
+    from b200qp import problems
+    P, q, A, l, u = problems.random_qp(N_VARS, N_CONS, nnz_per_row=NNZ_ROW, seed=SEED, band=64)
+    prob = osqp.OSQP(algebra="cuda")
+    prob.setup(P, q, A, l, u, verbose=False, **SOLVE_KW)
+    for _ in range(2):
+        prob.solve()
+    dev_ms, iters, cg, bytes_algo = 0.0, 0, 0, 0.0
+    steps = max(3, min(args.steps, 5))
+    for _ in range(steps):
+        res = prob.solve()
+        st = prob.stats()
+        dev_ms += st["kernel_ms"]; iters += st["admm_iters"]; cg += st["cg_iters"]; bytes_algo += st["algo_bytes"]
+    achieved = bytes_algo / (dev_ms * 1e-3) / 1e9
+    out = {"workload": f"random sparse QP n={N_VARS} m={N_CONS} nnz(A)={N_CONS * NNZ_ROW}, column indices within +-64 of the "
+                       f"diagonal (banded), seed {SEED}; cold-start solve() to eps 1e-3",
+           "value": iters / (dev_ms * 1e-3), "unit": UNIT, "ms_per_step": dev_ms / steps, "steps": steps,
+           "admm_iters_per_step": iters // steps, "pcg_iters_per_admm_iter": cg / max(iters, 1), "status": res.info.status,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "frac_of_8TBs": achieved / 8000.0}}
+    if not args.no_spmv:
+        out["spmv"] = spmv_line(A, peak)
+    return out
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     if world > 1:
@@ -268,6 +299,9 @@ def run_ours(args):
     }
     if not args.no_spmv:
         line["spmv"] = spmv_line(A, peak)
+    if not args.no_structured:
+        line["structured"] = structured_line(args, peak)
+        line["gpu_launches"] += 5
     if not args.no_batch:
         from b200qp import batchbench
         line["batch"] = batchbench.batch_line(args, with_cpu=not args.no_cpu_baseline)
@@ -288,6 +322,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spmv", action="store_true")
     ap.add_argument("--no-batch", action="store_true", help="skip the config-5 (batched MPC QPs) line")
+    ap.add_argument("--no-structured", action="store_true", help="skip the banded-sparsity counterpart of config 4")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

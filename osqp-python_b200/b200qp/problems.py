@@ -23,13 +23,18 @@ def _distinct_rows(cols, n):
     return cols
 
 
-def random_qp(n, m, nnz_per_row=10, seed=3, eq_frac=0.10, onesided_frac=0.0, p_pairs=1):
+def random_qp(n, m, nnz_per_row=10, seed=3, eq_frac=0.10, onesided_frac=0.0, p_pairs=1, band=None):
     """Configs 1 and 4: random sparse QP.  A has exactly `nnz_per_row` entries per row (the
     'diagonal' i mod n plus uniform random columns, N(0,1) values); P = diagonally dominant
-    symmetric matrix with diag in [0.1, 1.1] plus `p_pairs` symmetric off-diagonal pairs per row."""
+    symmetric matrix with diag in [0.1, 1.1] plus `p_pairs` symmetric off-diagonal pairs per row.
+    band=b keeps every column index within +-b of the row's diagonal position (same n, m, nnz; the
+    "sparsity with locality" counterpart of config 4 used by bench.py's structured line)."""
     rng = np.random.default_rng(seed)
     k = min(nnz_per_row, n)
-    cols = rng.integers(0, n, size=(m, k), dtype=np.int64)
+    if band is None:
+        cols = rng.integers(0, n, size=(m, k), dtype=np.int64)
+    else:
+        cols = (np.arange(m, dtype=np.int64)[:, None] % n + rng.integers(-band, band + 1, size=(m, k))) % n
     cols[:, 0] = np.arange(m) % n
     cols = _distinct_rows(cols, n).astype(np.int32)
     vals = rng.standard_normal((m, k))
@@ -38,7 +43,7 @@ def random_qp(n, m, nnz_per_row=10, seed=3, eq_frac=0.10, onesided_frac=0.0, p_p
     A.sort_indices()
     # P
     i = np.repeat(np.arange(n), p_pairs)
-    j = rng.integers(0, n, size=n * p_pairs)
+    j = rng.integers(0, n, size=n * p_pairs) if band is None else (i + rng.integers(-band, band + 1, size=n * p_pairs)) % n
     keep = i != j
     i, j = i[keep], j[keep]
     v = rng.uniform(-0.02, 0.02, size=i.size)
