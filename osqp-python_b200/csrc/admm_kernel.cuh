@@ -82,32 +82,53 @@ __device__ __forceinline__ double row_dot(const CsrMat& M, const double* xv, int
   return acc;
 }
 // two independent row dots (different rows of one matrix, or one row of two matrices) with their loads
-// interleaved: 4 index loads, then 4 gathers in flight per lane before the first FMA.
-template <int LG>
+// interleaved.  The persistent kernel is latency-bound (ncu: 70 % long-scoreboard stalls, IPC 0.74), so every
+// dependent round trip on the critical path counts: the first NP1 / NP2 entries of every lane are fetched in
+// straight-line code -- all index + value loads first, then all gathers, then the FMAs -- and only rows longer
+// than NP * LG entries enter the tail loop.  With 10 entries per row and 4 lanes, NP = 3 covers the whole row
+// (the previous version prefetched 2 and paid two more serial index -> gather round trips per row pair).
+// The row pointers come from the caller so that it can fetch those of the next pair one iteration ahead.
+// Summation order per lane: entries in index order (unchanged).
+template <int LG, int NP1, int NP2>
+__device__ __forceinline__ void dot_pair_ptr(const CsrMat& M1, const double* x1, int a1, int b1, const CsrMat& M2,
+                                             const double* x2, int a2, int b2, int lane, double& acc1, double& acc2) {
+  int j1[NP1], j2[NP2];
+  double v1[NP1], v2[NP2];
+#pragma unroll
+  for (int e = 0; e < NP1; ++e) {
+    const int k = a1 + lane + e * LG;
+    j1[e] = 0; v1[e] = 0.0;
+    if (k < b1) { j1[e] = ld_stream(M1.idx + k); v1[e] = ld_stream(M1.val + k); }
+  }
+#pragma unroll
+  for (int e = 0; e < NP2; ++e) {
+    const int k = a2 + lane + e * LG;
+    j2[e] = 0; v2[e] = 0.0;
+    if (k < b2) { j2[e] = ld_stream(M2.idx + k); v2[e] = ld_stream(M2.val + k); }
+  }
+  double y1[NP1], y2[NP2];
+#pragma unroll
+  for (int e = 0; e < NP1; ++e) y1[e] = (a1 + lane + e * LG < b1) ? ld_vec(x1 + j1[e]) : 0.0;
+#pragma unroll
+  for (int e = 0; e < NP2; ++e) y2[e] = (a2 + lane + e * LG < b2) ? ld_vec(x2 + j2[e]) : 0.0;
+  acc1 = v1[0] * y1[0];
+#pragma unroll
+  for (int e = 1; e < NP1; ++e) acc1 = fma(v1[e], y1[e], acc1);
+  acc2 = v2[0] * y2[0];
+#pragma unroll
+  for (int e = 1; e < NP2; ++e) acc2 = fma(v2[e], y2[e], acc2);
+#pragma unroll 4
+  for (int k = a1 + lane + NP1 * LG; k < b1; k += LG) acc1 = fma(ld_stream(M1.val + k), ld_vec(x1 + ld_stream(M1.idx + k)), acc1);
+#pragma unroll 4
+  for (int k = a2 + lane + NP2 * LG; k < b2; k += LG) acc2 = fma(ld_stream(M2.val + k), ld_vec(x2 + ld_stream(M2.idx + k)), acc2);
+}
+template <int LG, int NP1 = 3, int NP2 = 3>
 __device__ __forceinline__ void dot_pair(const CsrMat& M1, const double* x1, int row1, bool ok1, const CsrMat& M2,
                                          const double* x2, int row2, bool ok2, int lane, double& acc1, double& acc2) {
   int a1 = 0, b1 = 0, a2 = 0, b2 = 0;
   if (ok1) { a1 = __ldg(M1.ptr + row1); b1 = __ldg(M1.ptr + row1 + 1); }
   if (ok2) { a2 = __ldg(M2.ptr + row2); b2 = __ldg(M2.ptr + row2 + 1); }
-  const int k10 = a1 + lane, k11 = k10 + LG, k20 = a2 + lane, k21 = k20 + LG;
-  const bool h10 = k10 < b1, h11 = k11 < b1, h20 = k20 < b2, h21 = k21 < b2;
-  int j10 = 0, j11 = 0, j20 = 0, j21 = 0;
-  double v10 = 0.0, v11 = 0.0, v20 = 0.0, v21 = 0.0;
-  if (h10) { j10 = ld_stream(M1.idx + k10); v10 = ld_stream(M1.val + k10); }
-  if (h20) { j20 = ld_stream(M2.idx + k20); v20 = ld_stream(M2.val + k20); }
-  if (h11) { j11 = ld_stream(M1.idx + k11); v11 = ld_stream(M1.val + k11); }
-  if (h21) { j21 = ld_stream(M2.idx + k21); v21 = ld_stream(M2.val + k21); }
-  double y10 = 0.0, y11 = 0.0, y20 = 0.0, y21 = 0.0;
-  if (h10) y10 = ld_vec(x1 + j10);
-  if (h20) y20 = ld_vec(x2 + j20);
-  if (h11) y11 = ld_vec(x1 + j11);
-  if (h21) y21 = ld_vec(x2 + j21);
-  acc1 = fma(v11, y11, v10 * y10);
-  acc2 = fma(v21, y21, v20 * y20);
-#pragma unroll 4
-  for (int k = k11 + LG; k < b1; k += LG) acc1 = fma(ld_stream(M1.val + k), ld_vec(x1 + ld_stream(M1.idx + k)), acc1);
-#pragma unroll 4
-  for (int k = k21 + LG; k < b2; k += LG) acc2 = fma(ld_stream(M2.val + k), ld_vec(x2 + ld_stream(M2.idx + k)), acc2);
+  dot_pair_ptr<LG, NP1, NP2>(M1, x1, a1, b1, M2, x2, a2, b2, lane, acc1, acc2);
 }
 template <int LG>
 __device__ __forceinline__ void row_dot2(const CsrMat& M, const double* x1, const double* x2, int row, bool valid,
@@ -401,34 +422,62 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
     if (r0max > 1e-150) {
       const double tol = a.cg_tol_frac * r0max;
       for (int j = 0; j < a.cg_max_iter; ++j) {
-        // C1: w = rho .* (A p)
-        for (int base = m0; base < m1; base += 2 * NGM) {
-          const int rowA = base + grp_m, rowB = rowA + NGM;
-          const bool okA = rowA < m1, okB = rowB < m1;
-          double accA, accB;
-          dot_pair<LGM>(a.A, a.p, rowA, okA, a.A, a.p, rowB, okB, lane_m, accA, accB);
-          accA = group_sum<LGM>(accA);
-          accB = group_sum<LGM>(accB);
-          if (lane_m == 0) {
-            if (okA) a.w[rowA] = a.rho_v[rowA] * accA;
-            if (okB) a.w[rowB] = a.rho_v[rowB] * accB;
+        // C1: w = rho .* (A p)   (row pointers of the next pair are fetched one iteration ahead)
+        {
+          int pa0 = 0, pa1 = 0, pb0 = 0, pb1 = 0;
+          {
+            const int rowA = m0 + grp_m, rowB = rowA + NGM;
+            if (rowA < m1) { pa0 = __ldg(a.A.ptr + rowA); pa1 = __ldg(a.A.ptr + rowA + 1); }
+            if (rowB < m1) { pb0 = __ldg(a.A.ptr + rowB); pb1 = __ldg(a.A.ptr + rowB + 1); }
+          }
+          for (int base = m0; base < m1; base += 2 * NGM) {
+            const int rowA = base + grp_m, rowB = rowA + NGM;
+            const bool okA = rowA < m1, okB = rowB < m1;
+            const int ca0 = pa0, ca1 = pa1, cb0 = pb0, cb1 = pb1;
+            const int nA = rowA + 2 * NGM, nB = rowB + 2 * NGM;
+            pa0 = pa1 = pb0 = pb1 = 0;
+            if (nA < m1) { pa0 = __ldg(a.A.ptr + nA); pa1 = __ldg(a.A.ptr + nA + 1); }
+            if (nB < m1) { pb0 = __ldg(a.A.ptr + nB); pb1 = __ldg(a.A.ptr + nB + 1); }
+            double accA, accB;
+            dot_pair_ptr<LGM, 3, 3>(a.A, a.p, ca0, ca1, a.A, a.p, cb0, cb1, lane_m, accA, accB);
+            accA = group_sum<LGM>(accA);
+            accB = group_sum<LGM>(accB);
+            if (lane_m == 0) {
+              if (okA) a.w[rowA] = a.rho_v[rowA] * accA;
+              if (okB) a.w[rowB] = a.rho_v[rowB] * accB;
+            }
           }
         }
         B200QP_BARRIER_OR_DIE();
         mark(1);
         // C2: kp = P p + sigma p + A' w ; <p, kp>
         double v1[1] = {0.0};
-        for (int base = n0; base < n1; base += NGN) {
-          const int row = base + grp_n;
-          const bool valid = row < n1;
-          double accP, accA;
-          dot_pair<LGN>(a.P, a.p, row, valid, a.At, a.w, row, valid, lane_n, accP, accA);
-          const double acc = group_sum<LGN>(accP + accA);
-          if (valid && lane_n == 0) {
-            const double pj = a.p[row];
-            const double kpj = acc + sigma * pj;
-            a.kp[row] = kpj;
-            v1[0] += pj * kpj;
+        {
+          int pp0 = 0, pp1 = 0, pt0 = 0, pt1 = 0;
+          if (n0 + grp_n < n1) {
+            const int row = n0 + grp_n;
+            pp0 = __ldg(a.P.ptr + row); pp1 = __ldg(a.P.ptr + row + 1);
+            pt0 = __ldg(a.At.ptr + row); pt1 = __ldg(a.At.ptr + row + 1);
+          }
+          for (int base = n0; base < n1; base += NGN) {
+            const int row = base + grp_n;
+            const bool valid = row < n1;
+            const int cp0 = pp0, cp1 = pp1, ct0 = pt0, ct1 = pt1;
+            const int nr = row + NGN;
+            pp0 = pp1 = pt0 = pt1 = 0;
+            if (nr < n1) {
+              pp0 = __ldg(a.P.ptr + nr); pp1 = __ldg(a.P.ptr + nr + 1);
+              pt0 = __ldg(a.At.ptr + nr); pt1 = __ldg(a.At.ptr + nr + 1);
+            }
+            double accP, accA;
+            dot_pair_ptr<LGN, 1, 3>(a.P, a.p, cp0, cp1, a.At, a.w, ct0, ct1, lane_n, accP, accA);
+            const double acc = group_sum<LGN>(accP + accA);
+            if (valid && lane_n == 0) {
+              const double pj = a.p[row];
+              const double kpj = acc + sigma * pj;
+              a.kp[row] = kpj;
+              v1[0] += pj * kpj;
+            }
           }
         }
         double* bk = bank();

@@ -1251,7 +1251,7 @@ static void spmv_launch(b200qp_spmv_plan* pl, int variant) {
     k_spmv_scalar<<<cdiv(rows, 256), 256, 0, pl->stream>>>(M, pl->x.p, pl->y.p);
   } else {
     const int lg = pick_lg(rows ? (double)M.nnz / rows : 1.0);
-    const int grid = cdiv((long long)rows * lg, 256);
+    const int grid = cdiv((long long)((rows + 1) / 2) * lg, 256);   // two rows per lane group
     if (lg == 4) k_spmv_group<4><<<grid, 256, 0, pl->stream>>>(M, pl->x.p, pl->y.p);
     else if (lg == 8) k_spmv_group<8><<<grid, 256, 0, pl->stream>>>(M, pl->x.p, pl->y.p);
     else if (lg == 2) k_spmv_group<2><<<grid, 256, 0, pl->stream>>>(M, pl->x.p, pl->y.p);
