@@ -122,18 +122,6 @@ __device__ __forceinline__ void dot_pair_ptr(const CsrMat& M1, const double* x1,
 #pragma unroll 4
   for (int k = a2 + lane + NP2 * LG; k < b2; k += LG) acc2 = fma(ld_stream(M2.val + k), ld_vec(x2 + ld_stream(M2.idx + k)), acc2);
 }
-// L2 prefetch of the first NP entries per lane of a row whose pointers are already known (one row pair ahead of
-// the loads that use them): the index / value loads of the next iteration then hit L2 instead of paying the HBM
-// round trip on the critical path.  Costs no registers and no shared memory.
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-template <int LG, int NP>
-__device__ __forceinline__ void prefetch_row(const CsrMat& M, int a, int b, int lane) {
-#pragma unroll
-  for (int e = 0; e < NP; ++e) {
-    const int k = a + lane + e * LG;
-    if (k < b) { prefetch_l2(M.idx + k); prefetch_l2(M.val + k); }
-  }
-}
 template <int LG, int NP1 = 3, int NP2 = 3>
 __device__ __forceinline__ void dot_pair(const CsrMat& M1, const double* x1, int row1, bool ok1, const CsrMat& M2,
                                          const double* x2, int row2, bool ok2, int lane, double& acc1, double& acc2) {
@@ -434,23 +422,22 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
     if (r0max > 1e-150) {
       const double tol = a.cg_tol_frac * r0max;
       for (int j = 0; j < a.cg_max_iter; ++j) {
-        // C1: w = rho .* (A p).  Software pipeline over row pairs: pointers two pairs ahead, L2 prefetch of the
-        // index / value entries one pair ahead, loads + gathers + FMAs of the current pair.
+        // C1: w = rho .* (A p)   (row pointers of the next pair are fetched one iteration ahead)
         {
-          auto ptrs = [&](int row, int& p0, int& p1) {
-            p0 = 0; p1 = 0;
-            if (row < m1) { p0 = __ldg(a.A.ptr + row); p1 = __ldg(a.A.ptr + row + 1); }
-          };
-          int ca0, ca1, cb0, cb1, na0, na1, nb0, nb1;
-          ptrs(m0 + grp_m, ca0, ca1); ptrs(m0 + grp_m + NGM, cb0, cb1);
-          ptrs(m0 + grp_m + 2 * NGM, na0, na1); ptrs(m0 + grp_m + 3 * NGM, nb0, nb1);
+          int pa0 = 0, pa1 = 0, pb0 = 0, pb1 = 0;
+          {
+            const int rowA = m0 + grp_m, rowB = rowA + NGM;
+            if (rowA < m1) { pa0 = __ldg(a.A.ptr + rowA); pa1 = __ldg(a.A.ptr + rowA + 1); }
+            if (rowB < m1) { pb0 = __ldg(a.A.ptr + rowB); pb1 = __ldg(a.A.ptr + rowB + 1); }
+          }
           for (int base = m0; base < m1; base += 2 * NGM) {
             const int rowA = base + grp_m, rowB = rowA + NGM;
             const bool okA = rowA < m1, okB = rowB < m1;
-            int fa0, fa1, fb0, fb1;
-            ptrs(rowA + 4 * NGM, fa0, fa1); ptrs(rowB + 4 * NGM, fb0, fb1);
-            prefetch_row<LGM, 3>(a.A, na0, na1, lane_m);
-            prefetch_row<LGM, 3>(a.A, nb0, nb1, lane_m);
+            const int ca0 = pa0, ca1 = pa1, cb0 = pb0, cb1 = pb1;
+            const int nA = rowA + 2 * NGM, nB = rowB + 2 * NGM;
+            pa0 = pa1 = pb0 = pb1 = 0;
+            if (nA < m1) { pa0 = __ldg(a.A.ptr + nA); pa1 = __ldg(a.A.ptr + nA + 1); }
+            if (nB < m1) { pb0 = __ldg(a.A.ptr + nB); pb1 = __ldg(a.A.ptr + nB + 1); }
             double accA, accB;
             dot_pair_ptr<LGM, 3, 3>(a.A, a.p, ca0, ca1, a.A, a.p, cb0, cb1, lane_m, accA, accB);
             accA = group_sum<LGM>(accA);
@@ -459,8 +446,6 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
               if (okA) a.w[rowA] = a.rho_v[rowA] * accA;
               if (okB) a.w[rowB] = a.rho_v[rowB] * accB;
             }
-            ca0 = na0; ca1 = na1; cb0 = nb0; cb1 = nb1;
-            na0 = fa0; na1 = fa1; nb0 = fb0; nb1 = fb1;
           }
         }
         B200QP_BARRIER_OR_DIE();
@@ -468,23 +453,22 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
         // C2: kp = P p + sigma p + A' w ; <p, kp>
         double v1[1] = {0.0};
         {
-          auto ptrs = [&](int row, int& p0, int& p1, int& t0, int& t1) {
-            p0 = 0; p1 = 0; t0 = 0; t1 = 0;
-            if (row < n1) {
-              p0 = __ldg(a.P.ptr + row); p1 = __ldg(a.P.ptr + row + 1);
-              t0 = __ldg(a.At.ptr + row); t1 = __ldg(a.At.ptr + row + 1);
-            }
-          };
-          int cp0, cp1, ct0, ct1, np0, np1, nt0, nt1;
-          ptrs(n0 + grp_n, cp0, cp1, ct0, ct1);
-          ptrs(n0 + grp_n + NGN, np0, np1, nt0, nt1);
+          int pp0 = 0, pp1 = 0, pt0 = 0, pt1 = 0;
+          if (n0 + grp_n < n1) {
+            const int row = n0 + grp_n;
+            pp0 = __ldg(a.P.ptr + row); pp1 = __ldg(a.P.ptr + row + 1);
+            pt0 = __ldg(a.At.ptr + row); pt1 = __ldg(a.At.ptr + row + 1);
+          }
           for (int base = n0; base < n1; base += NGN) {
             const int row = base + grp_n;
             const bool valid = row < n1;
-            int fp0, fp1, ft0, ft1;
-            ptrs(row + 2 * NGN, fp0, fp1, ft0, ft1);
-            prefetch_row<LGN, 1>(a.P, np0, np1, lane_n);
-            prefetch_row<LGN, 3>(a.At, nt0, nt1, lane_n);
+            const int cp0 = pp0, cp1 = pp1, ct0 = pt0, ct1 = pt1;
+            const int nr = row + NGN;
+            pp0 = pp1 = pt0 = pt1 = 0;
+            if (nr < n1) {
+              pp0 = __ldg(a.P.ptr + nr); pp1 = __ldg(a.P.ptr + nr + 1);
+              pt0 = __ldg(a.At.ptr + nr); pt1 = __ldg(a.At.ptr + nr + 1);
+            }
             double accP, accA;
             dot_pair_ptr<LGN, 1, 3>(a.P, a.p, cp0, cp1, a.At, a.w, ct0, ct1, lane_n, accP, accA);
             const double acc = group_sum<LGN>(accP + accA);
@@ -494,8 +478,6 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
               a.kp[row] = kpj;
               v1[0] += pj * kpj;
             }
-            cp0 = np0; cp1 = np1; ct0 = nt0; ct1 = nt1;
-            np0 = fp0; np1 = fp1; nt0 = ft0; nt1 = ft1;
           }
         }
         double* bk = bank();
