@@ -122,6 +122,37 @@ __device__ __forceinline__ void dot_pair_ptr(const CsrMat& M1, const double* x1,
 #pragma unroll 4
   for (int k = a2 + lane + NP2 * LG; k < b2; k += LG) acc2 = fma(ld_stream(M2.val + k), ld_vec(x2 + ld_stream(M2.idx + k)), acc2);
 }
+// NR independent rows of ONE matrix against one vector, same scheme: all index + value loads, then all gathers,
+// then the FMAs (entries in index order per lane); rows longer than NP * LG entries finish in a tail loop.
+template <int LG, int NP, int NR>
+__device__ __forceinline__ void dot_rows(const CsrMat& M, const double* xv, const int (&ra)[NR], const int (&rb)[NR], int lane,
+                                         double (&acc)[NR]) {
+  int j[NR][NP];
+  double v[NR][NP], y[NR][NP];
+#pragma unroll
+  for (int e = 0; e < NP; ++e)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int k = ra[r] + lane + e * LG;
+      j[r][e] = 0; v[r][e] = 0.0;
+      if (k < rb[r]) { j[r][e] = ld_stream(M.idx + k); v[r][e] = ld_stream(M.val + k); }
+    }
+#pragma unroll
+  for (int e = 0; e < NP; ++e)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) y[r][e] = (ra[r] + lane + e * LG < rb[r]) ? ld_vec(xv + j[r][e]) : 0.0;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    acc[r] = v[r][0] * y[r][0];
+#pragma unroll
+    for (int e = 1; e < NP; ++e) acc[r] = fma(v[r][e], y[r][e], acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+#pragma unroll 4
+    for (int k = ra[r] + lane + NP * LG; k < rb[r]; k += LG) acc[r] = fma(ld_stream(M.val + k), ld_vec(xv + ld_stream(M.idx + k)), acc[r]);
+  }
+}
 template <int LG, int NP1 = 3, int NP2 = 3>
 __device__ __forceinline__ void dot_pair(const CsrMat& M1, const double* x1, int row1, bool ok1, const CsrMat& M2,
                                          const double* x2, int row2, bool ok2, int lane, double& acc1, double& acc2) {
@@ -252,7 +283,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
           px = row_dot<LGN>(a.P, a.x, row, valid, lane_n);
           row_dot2<LGN>(a.At, a.w2, a.y, row, valid, lane_n, atw, aty);
         } else {
-          dot_pair<LGN>(a.P, a.x, row, valid, a.At, a.w2, row, valid, lane_n, px, atw);
+          dot_pair<LGN, 1, 4>(a.P, a.x, row, valid, a.At, a.w2, row, valid, lane_n, px, atw);
         }
         px = group_sum<LGN>(px);
         if (full) aty = group_sum<LGN>(aty);
@@ -422,29 +453,34 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
     if (r0max > 1e-150) {
       const double tol = a.cg_tol_frac * r0max;
       for (int j = 0; j < a.cg_max_iter; ++j) {
-        // C1: w = rho .* (A p)   (row pointers of the next pair are fetched one iteration ahead)
+        // C1: w = rho .* (A p): C1_NR rows per lane group and iteration (row pointers of the next set are fetched
+        // one iteration ahead); with 4 lanes and 3 entries per lane that is 9 index + 9 value loads, then 9 gathers,
+        // in flight per lane
         {
-          int pa0 = 0, pa1 = 0, pb0 = 0, pb1 = 0;
-          {
-            const int rowA = m0 + grp_m, rowB = rowA + NGM;
-            if (rowA < m1) { pa0 = __ldg(a.A.ptr + rowA); pa1 = __ldg(a.A.ptr + rowA + 1); }
-            if (rowB < m1) { pb0 = __ldg(a.A.ptr + rowB); pb1 = __ldg(a.A.ptr + rowB + 1); }
+          constexpr int C1_NR = 2;   // 3 rows measured slower (40.0 vs 36.7 ms per solve: register pressure at the 64-register cap)
+          int na[C1_NR], nb[C1_NR];
+#pragma unroll
+          for (int r = 0; r < C1_NR; ++r) {
+            const int row = m0 + grp_m + r * NGM;
+            na[r] = 0; nb[r] = 0;
+            if (row < m1) { na[r] = __ldg(a.A.ptr + row); nb[r] = __ldg(a.A.ptr + row + 1); }
           }
-          for (int base = m0; base < m1; base += 2 * NGM) {
-            const int rowA = base + grp_m, rowB = rowA + NGM;
-            const bool okA = rowA < m1, okB = rowB < m1;
-            const int ca0 = pa0, ca1 = pa1, cb0 = pb0, cb1 = pb1;
-            const int nA = rowA + 2 * NGM, nB = rowB + 2 * NGM;
-            pa0 = pa1 = pb0 = pb1 = 0;
-            if (nA < m1) { pa0 = __ldg(a.A.ptr + nA); pa1 = __ldg(a.A.ptr + nA + 1); }
-            if (nB < m1) { pb0 = __ldg(a.A.ptr + nB); pb1 = __ldg(a.A.ptr + nB + 1); }
-            double accA, accB;
-            dot_pair_ptr<LGM, 3, 3>(a.A, a.p, ca0, ca1, a.A, a.p, cb0, cb1, lane_m, accA, accB);
-            accA = group_sum<LGM>(accA);
-            accB = group_sum<LGM>(accB);
-            if (lane_m == 0) {
-              if (okA) a.w[rowA] = a.rho_v[rowA] * accA;
-              if (okB) a.w[rowB] = a.rho_v[rowB] * accB;
+          for (int base = m0; base < m1; base += C1_NR * NGM) {
+            int ca[C1_NR], cb[C1_NR];
+#pragma unroll
+            for (int r = 0; r < C1_NR; ++r) {
+              ca[r] = na[r]; cb[r] = nb[r];
+              const int nrow = base + grp_m + (r + C1_NR) * NGM;
+              na[r] = 0; nb[r] = 0;
+              if (nrow < m1) { na[r] = __ldg(a.A.ptr + nrow); nb[r] = __ldg(a.A.ptr + nrow + 1); }
+            }
+            double acc[C1_NR];
+            dot_rows<LGM, 3, C1_NR>(a.A, a.p, ca, cb, lane_m, acc);
+#pragma unroll
+            for (int r = 0; r < C1_NR; ++r) {
+              const double sacc = group_sum<LGM>(acc[r]);
+              const int row = base + grp_m + r * NGM;
+              if (lane_m == 0 && row < m1) a.w[row] = a.rho_v[row] * sacc;
             }
           }
         }
@@ -470,7 +506,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
               pt0 = __ldg(a.At.ptr + nr); pt1 = __ldg(a.At.ptr + nr + 1);
             }
             double accP, accA;
-            dot_pair_ptr<LGN, 1, 3>(a.P, a.p, cp0, cp1, a.At, a.w, ct0, ct1, lane_n, accP, accA);
+            dot_pair_ptr<LGN, 1, 4>(a.P, a.p, cp0, cp1, a.At, a.w, ct0, ct1, lane_n, accP, accA);
             const double acc = group_sum<LGN>(accP + accA);
             if (valid && lane_n == 0) {
               const double pj = a.p[row];
