@@ -44,6 +44,8 @@ struct BArgs {
   double *xs, *zs, *ys, *rho_b;                      // per-QP ADMM state, scaled space (kept between solves)
   double *sol_x, *sol_y, *cert_n, *cert_m;           // [batch][n | m], unscaled results
   double *kcache, *rcache;                           // dense mode, per CTA: K^-1 [n * ldk] of the last cold rho vector [m]
+  const double *Pv, *Av, *Atv, *pdv;                 // per-element scaled matrix values [batch][nnz] (per_mat), else unused
+  int per_mat;
   BInfo* info;
   int* next;                                         // work counter
   double sigma, alpha, eps_abs, eps_rel, eps_pinf, eps_dinf, c, adapt_tol, cg_tol_frac, rho_eq_factor, time_limit_ns;
@@ -294,6 +296,13 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
     if (qp >= a.batch) break;
     const unsigned long long t_start = global_timer_ns();
     const size_t on = (size_t)qp * n, om = (size_t)qp * m;
+    // matrices of this element: shared pattern, shared or per-element values
+    CsrMat P = a.P, A = a.A, At = a.At;
+    const double* pdiag = a.pdiag;
+    if (a.per_mat) {
+      P.val = a.Pv + (size_t)qp * P.nnz; A.val = a.Av + (size_t)qp * A.nnz; At.val = a.Atv + (size_t)qp * At.nnz;
+      pdiag = a.pdv + on;
+    }
 
     // ---------------------------------------------------------------- load the QP
     double rho = a.rho_b[qp];
@@ -325,14 +334,14 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
       const int row = base + grp_n;
       const bool valid = row < n;
       const bool jac = a.cg_precond && !DENSE;
-      double ms = jac ? brow_dot_sq<LGN>(a.At, rho_v, row, valid, lane_n) : 0.0;
+      double ms = jac ? brow_dot_sq<LGN>(At, rho_v, row, valid, lane_n) : 0.0;
       ms = group_sum<LGN>(ms);
-      if (valid && lane_n == 0) Minv[row] = jac ? 1.0 / (__ldg(a.pdiag + row) + sigma + ms) : 1.0;
+      if (valid && lane_n == 0) Minv[row] = jac ? 1.0 / (__ldg(pdiag + row) + sigma + ms) : 1.0;
     }
     for (int base = 0; base < m; base += NGM) {
       const int row = base + grp_m;
       const bool valid = row < m;
-      const double acc = group_sum<LGM>(a.warm ? brow_dot<LGM>(a.A, x, row, valid, lane_m) : 0.0);
+      const double acc = group_sum<LGM>(a.warm ? brow_dot<LGM>(A, x, row, valid, lane_m) : 0.0);
       if (valid && lane_m == 0) {
         ax[row] = acc;
         w2[row] = rho_v[row] * (z[row] - acc) - y[row];
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
     // ---- dense mode: K = P + sigma I + A' rho A formed row by row (thread j owns row j: no atomics), inverted
     // in place by Gauss-Jordan elimination without pivoting (K is SPD; a non-positive pivot means it is not)
     auto build_inverse = [&]() -> bool {
-      if constexpr (DENSE) return dense_build_inverse<NTB>(a.P, a.A, a.At, (int)(rho_v - sm), sigma, n, LDK, (int)(Kinv - sm), (int)(rowk - sm)) != 0;
+      if constexpr (DENSE) return dense_build_inverse<NTB>(P, A, At, (int)(rho_v - sm), sigma, n, LDK, (int)(Kinv - sm), (int)(rowk - sm)) != 0;
       else return true;
     };
     // d = K^-1 r  (K^-1 symmetric: thread (part, j) walks column j = row j with unit-stride lanes)
@@ -382,7 +391,7 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
       // re-loads it -- 0.1 MB from L2 instead of n Gauss-Jordan steps -- whenever the rho vector matches.
       double* kc = a.kcache + (size_t)blockIdx.x * n * LDK;
       double* rc = a.rcache + (size_t)blockIdx.x * m;
-      int same = have_cache;
+      int same = have_cache && !a.per_mat;
       if (have_cache)
         for (int i = tid; i < m; i += NTB) same = same && (rc[i] == rho_v[i]);
       same = __syncthreads_and(same);
@@ -391,7 +400,7 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
         __syncthreads();
       } else {
         if (!build_inverse()) status = 9;
-        if (!have_cache && status == 0) {
+        if (!have_cache && !a.per_mat && status == 0) {
           for (int e = tid; e < n * LDK; e += NTB) kc[e] = Kinv[e];
           for (int i = tid; i < m; i += NTB) rc[i] = rho_v[i];
           have_cache = 1;
@@ -411,13 +420,13 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
         const bool valid = row < n;
         double pxv = 0, atw = 0, aty = 0, msum = 0;
         if (lite) {
-          atw = brow_dot<LGN>(a.At, w2, row, valid, lane_n);
-          if (a.cg_precond && !DENSE) msum = brow_dot_sq<LGN>(a.At, rho_v, row, valid, lane_n);
+          atw = brow_dot<LGN>(At, w2, row, valid, lane_n);
+          if (a.cg_precond && !DENSE) msum = brow_dot_sq<LGN>(At, rho_v, row, valid, lane_n);
           msum = group_sum<LGN>(msum);
         } else {
-          pxv = brow_dot<LGN>(a.P, x, row, valid, lane_n);
-          if (full) brow_dot2<LGN>(a.At, w2, y, row, valid, lane_n, atw, aty);
-          else atw = brow_dot<LGN>(a.At, w2, row, valid, lane_n);
+          pxv = brow_dot<LGN>(P, x, row, valid, lane_n);
+          if (full) brow_dot2<LGN>(At, w2, y, row, valid, lane_n, atw, aty);
+          else atw = brow_dot<LGN>(At, w2, row, valid, lane_n);
           pxv = group_sum<LGN>(pxv);
           if (full) aty = group_sum<LGN>(aty);
         }
@@ -426,7 +435,7 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
           const double qj = q[row];
           if (lite) {
             pxv = px[row];
-            if (a.cg_precond && !DENSE) Minv[row] = 1.0 / (__ldg(a.pdiag + row) + sigma + msum);
+            if (a.cg_precond && !DENSE) Minv[row] = 1.0 / (__ldg(pdiag + row) + sigma + msum);
           }
           const double rj = -(pxv + qj) + atw;
           const double pj = Minv[row] * rj;
@@ -501,14 +510,14 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
       if (!prim_ok) {
         const double eps = f * a.eps_pinf;
         if (ndy > eps && lhs < -eps * ndy) {
-          const double nat = cert_norm(a.At, w, 1.0);
+          const double nat = cert_norm(At, w, 1.0);
           if (nat < eps * ndy) return f > 1.0 ? 4 : 3;
         }
       }
       if (!dual_ok) {
         const double eps = f * a.eps_dinf;
         if (ndx > eps && qdx < -c_eff * eps * ndx && vu <= eps * ndx && vl <= eps * ndx) {
-          const double npd = cert_norm(a.P, d, alpha);
+          const double npd = cert_norm(P, d, alpha);
           if (npd < c_eff * eps * ndx) return f > 1.0 ? 6 : 5;
         }
       }
@@ -562,7 +571,7 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
           for (int base = 0; base < m; base += NGM) {
             const int row = base + grp_m;
             const bool valid = row < m;
-            const double acc = group_sum<LGM>(brow_dot<LGM>(a.A, p, row, valid, lane_m));
+            const double acc = group_sum<LGM>(brow_dot<LGM>(A, p, row, valid, lane_m));
             if (valid && lane_m == 0) w[row] = rho_v[row] * acc;
           }
           __syncthreads();
@@ -571,7 +580,7 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
           for (int base = 0; base < n; base += NGN) {
             const int row = base + grp_n;
             const bool valid = row < n;
-            const double acc = group_sum<LGN>(brow_dot<LGN>(a.P, p, row, valid, lane_n) + brow_dot<LGN>(a.At, w, row, valid, lane_n));
+            const double acc = group_sum<LGN>(brow_dot<LGN>(P, p, row, valid, lane_n) + brow_dot<LGN>(At, w, row, valid, lane_n));
             if (valid && lane_n == 0) {
               const double pj = p[row];
               const double kpj = acc + sigma * pj;
@@ -629,7 +638,7 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
         for (int base = 0; base < m; base += NGM) {
           const int row = base + grp_m;
           const bool valid = row < m;
-          const double ad = group_sum<LGM>(brow_dot<LGM>(a.A, d, row, valid, lane_m));
+          const double ad = group_sum<LGM>(brow_dot<LGM>(A, d, row, valid, lane_m));
           if (valid && lane_m == 0) {
             const double ax_old = ax[row], z_old = z[row], y_old = y[row];
             const double rv = rho_v[row], ri = 1.0 / rv, li = l[row], ui = u[row];

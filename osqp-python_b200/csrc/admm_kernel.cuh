@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
       const double tol = a.cg_tol_frac * r0max;
       for (int j = 0; j < a.cg_max_iter; ++j) {
         // C1: w = rho .* (A p): C1_NR rows per lane group and iteration (row pointers of the next set are fetched
-        // one iteration ahead); with 4 lanes and 3 entries per lane that is 9 index + 9 value loads, then 9 gathers,
+        // one iteration ahead); with 3 entries per lane that is 3 C1_NR index + value loads, then 3 C1_NR gathers,
         // in flight per lane
         {
           constexpr int C1_NR = 2;   // 3 rows measured slower (40.0 vs 36.7 ms per solve: register pressure at the 64-register cap)

@@ -842,6 +842,8 @@ int b200qp_internal_view(const b200qp_solver* solver, b200qp::InternalView* v) {
   v->P = w->P.view(); v->A = w->A.view(); v->At = w->At.view();
   v->pdiag = w->pdiag.p; v->D = w->D.p; v->Dinv = w->Dinv.p; v->E = w->E.p; v->Einv = w->Einv.p;
   v->c = w->c; v->rho_eq_factor = w->rho_eq_factor;
+  v->mapA = w->mapA.p; v->Pt_colptr = w->Pt_colptr.p; v->Pt_rowidx = w->Pt_rowidx.p; v->posU = w->posU.p; v->posL = w->posL.p;
+  v->nnzPt = w->nnzPt;
   return 0;
 }
 

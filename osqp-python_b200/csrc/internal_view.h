@@ -11,6 +11,9 @@ struct InternalView {
   CsrMat P, A, At;                          // scaled: c D P D (full symmetric CSR), E A D, D A' E
   const double *pdiag, *D, *Dinv, *E, *Einv;
   double c, rho_eq_factor;
+  // value-update maps (b200qp_update_data_mat): triu-CSC(P) position -> both CSR(P) positions, CSC(A) -> CSR(A)
+  const int *mapA, *Pt_colptr, *Pt_rowidx, *posU, *posL;
+  int nnzPt;
 };
 }  // namespace b200qp
 
