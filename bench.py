@@ -48,10 +48,10 @@ NNZ_ROW = 10
 SEED = 3
 ENGINE_SPEC = dict(cg_max_iter=100, cg_tol_fraction=0.1, rho_eq_factor=10.0)   # the engine's defaults, for the CPU port
 # dram__bytes_read.sum + dram__bytes_write.sum of one admm_kernel launch of this workload, from the committed
-# `ncu --set full` capture (234.72 GB + 12.15 GB; the n- and m-vectors stay L2-resident, so it is below the
+# `ncu --set full` capture (231.88 GB + 12.23 GB; the n- and m-vectors stay L2-resident, so it is below the
 # algorithmic byte count); only valid for the default problem size
-NCU_TRAFFIC_BYTES = 246.866e9 if (N_VARS, N_CONS) == (1_000_000, 1_000_000) else None
-NCU_TRAFFIC_SOURCE = "profiles/r1c_admm_kernel_ncu_raw.csv (75 ADMM / 642 PCG iterations per launch)"
+NCU_TRAFFIC_BYTES = 244.110e9 if (N_VARS, N_CONS) == (1_000_000, 1_000_000) else None
+NCU_TRAFFIC_SOURCE = "profiles/r1d_admm_kernel_ncu_raw.csv (75 ADMM / 642 PCG iterations per launch)"
 SOLVE_KW = dict(eps_abs=1e-3, eps_rel=1e-3, max_iter=4000, warm_starting=False, polishing=False)
 
 

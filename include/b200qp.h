@@ -226,7 +226,8 @@ b200qp_int b200qp_dist_solve_group(b200qp_solver **group, b200qp_int world);
  * solve() -- same scaling (D, E, c of element 0; update() never re-equilibrates, _osqp.py:1312-1367), own
  * ADMM state and own rho.  q is batch x n, l and u are batch x m, row-major, HOST buffers consumed before
  * the call returns.  Multi-GPU: one b200qp_batch per GPU (settings->device) over a shard of the batch; no
- * collective.  Polish is not run on batch elements (status_polish stays 0). */
+ * collective.  Polish is not run on batch elements (status_polish stays 0).  Matrix VALUES may also differ per
+ * element (b200qp_batch_update_data_mat); the sparsity pattern is shared. */
 typedef struct b200qp_batch b200qp_batch;
 typedef struct {            /* per element; mirrors the OSQPInfo fields that are per solve */
   b200qp_int status_val, iter, rho_updates, cg_iter;
@@ -245,6 +246,11 @@ b200qp_int b200qp_batch_setup(b200qp_batch **batchp, b200qp_int batch, const b20
 b200qp_int b200qp_batch_solve(b200qp_batch *b);
 b200qp_int b200qp_batch_update_data_vec(b200qp_batch *b, const b200qp_float *q_new, const b200qp_float *l_new,
                                         const b200qp_float *u_new);
+/* per-element matrix values on the shared pattern (the reference's batched caller passes P_val / A_val per
+ * element, src/osqp/nn/torch.py:136-140): Px_new is batch x nnz(triu P), Ax_new is batch x nnz(A), CSC order,
+ * unscaled, either may be NULL.  Same semantics as osqp_update_data_mat without index arrays
+ * (src/bindings.cpp.in:240-281): the scaling of the setup is kept. */
+b200qp_int b200qp_batch_update_data_mat(b200qp_batch *b, const b200qp_float *Px_new, const b200qp_float *Ax_new);
 b200qp_int b200qp_batch_warm_start(b200qp_batch *b, const b200qp_float *x, const b200qp_float *y);
 b200qp_int b200qp_batch_update_settings(b200qp_batch *b, const b200qp_settings *new_settings);
 b200qp_int b200qp_batch_update_rho(b200qp_batch *b, b200qp_float rho_new);

@@ -62,6 +62,45 @@ __global__ void kb_spmv(CsrMat A, int batch, const double* __restrict__ xs, doub
   if (g < rows && lane == 0) zs[b * A.rows + row] = acc;
 }
 
+// dst[b][i] = src[i]  (replicate the shared scaled values before the first per-element update)
+__global__ void kb_tile_rows(long long total, int len, double* __restrict__ dst, const double* __restrict__ src) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < total) dst[t] = src[t % len];
+}
+// per-element A values, UNSCALED, CSC order [batch][nnzA] -> scaled CSR(A') (same order) and CSR(A) (mapA)
+// (single-solver counterpart: k_update_A in aux_kernels.cuh; reference _osqp.py:1455-1470)
+__global__ void kb_update_A(long long total, int nnz, const double* __restrict__ vals, const int* __restrict__ colptr,
+                            const int* __restrict__ rowidx, int ncols, const int* __restrict__ mapA,
+                            const double* __restrict__ D, const double* __restrict__ E, double* __restrict__ Atv,
+                            double* __restrict__ Av) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const long long b = t / nnz;
+  const int k = (int)(t % nnz);
+  int lo = 0, hi = ncols;               // column j with colptr[j] <= k < colptr[j+1]
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (colptr[mid] <= k) lo = mid; else hi = mid; }
+  const double v = E[rowidx[k]] * vals[t] * D[lo];
+  Atv[b * nnz + k] = v;
+  Av[b * nnz + mapA[k]] = v;
+}
+// per-element P values, UNSCALED, upper triangle in CSC order [batch][nnzPt] -> both mirrored positions of the
+// full CSR values [batch][nnzP] and the diagonal [batch][n]  (k_update_P; reference _osqp.py:1437-1452)
+__global__ void kb_update_P(long long total, int nnzPt, int nnzP, int n, const double* __restrict__ vals,
+                            const int* __restrict__ colptr, const int* __restrict__ rowidx,
+                            const int* __restrict__ posU, const int* __restrict__ posL, const double* __restrict__ D,
+                            double c, double* __restrict__ Pv, double* __restrict__ pdv) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const long long b = t / nnzPt;
+  const int k = (int)(t % nnzPt);
+  int lo = 0, hi = n;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (colptr[mid] <= k) lo = mid; else hi = mid; }
+  const int i = rowidx[k];
+  const double v = c * D[i] * vals[t] * D[lo];
+  Pv[b * nnzP + posU[k]] = v;
+  if (posL[k] >= 0) Pv[b * nnzP + posL[k]] = v; else pdv[b * n + i] = v;
+}
+
 typedef void (*batch_fn)(const BArgs);
 int pick_blg(double avg) { return avg <= 12.0 ? 4 : 16; }
 batch_fn pick_batch_kernel(int lgn, int lgm, bool dense, int nt) {
@@ -96,6 +135,8 @@ struct b200qp_batch {
   double *sol_x = nullptr, *sol_y = nullptr, *cert_n = nullptr, *cert_m = nullptr;
   double* stage = nullptr;                                      // batch * max(n, m) doubles
   double *kcache = nullptr, *rcache = nullptr;                  // dense mode: per-CTA inverse cache
+  double *Pv = nullptr, *Av = nullptr, *Atv = nullptr, *pdv = nullptr, *stage_mat = nullptr;   // per-element matrix values
+  bool per_mat = false;
   BInfo* info = nullptr;
   int* next = nullptr;
   // pinned host mirrors of the last solve
@@ -109,7 +150,7 @@ struct b200qp_batch {
 
   ~b200qp_batch() {
     cudaSetDevice(device);
-    for (double* p : {q, l, u, xs, zs, ys, rho_b, sol_x, sol_y, cert_n, cert_m, stage, kcache, rcache})
+    for (double* p : {q, l, u, xs, zs, ys, rho_b, sol_x, sol_y, cert_n, cert_m, stage, kcache, rcache, Pv, Av, Atv, pdv, stage_mat})
       if (p) cudaFree(p);
     if (info) cudaFree(info);
     if (next) cudaFree(next);
@@ -268,6 +309,7 @@ b200qp_int b200qp_batch_solve(b200qp_batch* b) {
     a.sol_x = b->sol_x; a.sol_y = b->sol_y; a.cert_n = b->cert_n; a.cert_m = b->cert_m;
     a.info = b->info; a.next = b->next;
     a.kcache = b->kcache; a.rcache = b->rcache;
+    a.Pv = b->Pv; a.Av = b->Av; a.Atv = b->Atv; a.pdv = b->pdv; a.per_mat = b->per_mat ? 1 : 0;
     a.sigma = st->sigma; a.alpha = st->alpha; a.eps_abs = st->eps_abs; a.eps_rel = st->eps_rel;
     a.eps_pinf = st->eps_prim_inf; a.eps_dinf = st->eps_dual_inf; a.c = b->v.c; a.adapt_tol = st->adaptive_rho_tolerance;
     a.cg_tol_frac = st->cg_tol_fraction; a.rho_eq_factor = b->v.rho_eq_factor; a.time_limit_ns = st->time_limit * 1e9;
@@ -342,6 +384,49 @@ b200qp_int b200qp_batch_update_data_vec(b200qp_batch* b, const b200qp_float* q_n
     if (q_new) { upload_scaled(b, q_new, b->n, b->q, b->v.D, b->v.c); BCK(cudaStreamSynchronize(b->stream)); }
     if (l_new && bm) { upload_scaled(b, l_new, b->m, b->l, b->v.E, 1.0); BCK(cudaStreamSynchronize(b->stream)); }
     if (u_new && bm) { upload_scaled(b, u_new, b->m, b->u, b->v.E, 1.0); BCK(cudaStreamSynchronize(b->stream)); }
+    for (int i = 0; i < b->batch; ++i) b->h_info[i].status = B200QP_UNSOLVED;
+  } catch (int code) {
+    return code;
+  }
+  b->stats.update_time = now_s() - t0;
+  return 0;
+}
+
+b200qp_int b200qp_batch_update_data_mat(b200qp_batch* b, const b200qp_float* Px_new, const b200qp_float* Ax_new) {
+  if (!b || !b->proto) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  if (!Px_new && !Ax_new) return 0;
+  const double t0 = now_s();
+  try {
+    BCK(cudaSetDevice(b->device));
+    const InternalView& v = b->v;
+    const long long B = b->batch;
+    const int n = b->n, nnzP = v.P.nnz, nnzA = v.A.nnz, nnzPt = v.nnzPt;
+    if (!b->per_mat) {
+      // first per-element update: every element starts from the shared (scaled) values of the setup
+      b->Pv = dalloc((size_t)B * std::max(nnzP, 1)); b->Av = dalloc((size_t)B * std::max(nnzA, 1));
+      b->Atv = dalloc((size_t)B * std::max(nnzA, 1)); b->pdv = dalloc((size_t)B * n);
+      b->stage_mat = dalloc((size_t)B * std::max(std::max(nnzPt, nnzA), 1));
+      if (nnzP) kb_tile_rows<<<cdiv(B * nnzP, 256), 256, 0, b->stream>>>(B * nnzP, nnzP, b->Pv, v.P.val);
+      if (nnzA) {
+        kb_tile_rows<<<cdiv(B * nnzA, 256), 256, 0, b->stream>>>(B * nnzA, nnzA, b->Av, v.A.val);
+        kb_tile_rows<<<cdiv(B * nnzA, 256), 256, 0, b->stream>>>(B * nnzA, nnzA, b->Atv, v.At.val);
+      }
+      kb_tile_rows<<<cdiv(B * n, 256), 256, 0, b->stream>>>(B * n, n, b->pdv, v.pdiag);
+      b->per_mat = true;
+    }
+    if (Px_new && nnzPt) {
+      BCK(cudaMemcpyAsync(b->stage_mat, Px_new, (size_t)B * nnzPt * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+      kb_update_P<<<cdiv(B * nnzPt, 256), 256, 0, b->stream>>>(B * nnzPt, nnzPt, nnzP, n, b->stage_mat, v.Pt_colptr, v.Pt_rowidx,
+                                                               v.posU, v.posL, v.D, v.c, b->Pv, b->pdv);
+      BCK(cudaStreamSynchronize(b->stream));
+    }
+    if (Ax_new && nnzA) {
+      BCK(cudaMemcpyAsync(b->stage_mat, Ax_new, (size_t)B * nnzA * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+      kb_update_A<<<cdiv(B * nnzA, 256), 256, 0, b->stream>>>(B * nnzA, nnzA, b->stage_mat, v.At.ptr, v.At.idx, n, v.mapA, v.D, v.E,
+                                                              b->Atv, b->Av);
+      BCK(cudaStreamSynchronize(b->stream));
+    }
+    BCK(cudaStreamSynchronize(b->stream));
     for (int i = 0; i < b->batch; ++i) b->h_info[i].status = B200QP_UNSOLVED;
   } catch (int code) {
     return code;

@@ -175,7 +175,7 @@ class BatchSolver {
  public:
   BatchSolver(const CscHandle& P, py::object q, const CscHandle& A, py::object l, py::object u, b200qp_int batch,
               b200qp_int m, b200qp_int n, const b200qp_settings* settings)
-      : batch_(batch), m_(m), n_(n) {
+      : batch_(batch), m_(m), n_(n), nnzP_(P.nzmax), nnzA_(A.nzmax) {
     darray qc = darray::ensure(q), lc = darray::ensure(l), uc = darray::ensure(u);
     if (!qc || !lc || !uc || batch <= 0 || qc.size() != (py::ssize_t)batch * n || lc.size() != (py::ssize_t)batch * m ||
         uc.size() != (py::ssize_t)batch * m)
@@ -209,6 +209,16 @@ class BatchSolver {
     const b200qp_float* pu = opt_batch(u, ku, m_);
     py::gil_scoped_release nogil;
     return b200qp_batch_update_data_vec(b_, pq, pl, pu);
+  }
+  b200qp_int update_data_mat(py::object Px, py::object Ax) {
+    darray kp, ka;
+    const b200qp_float* pp = opt_doubles(Px, kp);
+    const b200qp_float* pa = opt_doubles(Ax, ka);
+    if ((pp && (kp.ndim() != 2 || kp.shape(0) != batch_ || kp.shape(1) != nnzP_)) ||
+        (pa && (ka.ndim() != 2 || ka.shape(0) != batch_ || ka.shape(1) != nnzA_)))
+      throw py::value_error(std::to_string(B200QP_DATA_VALIDATION_ERROR));
+    py::gil_scoped_release nogil;
+    return b200qp_batch_update_data_mat(b_, pp, pa);
   }
   b200qp_int warm_start(py::object x, py::object y) {
     darray kx, ky;
@@ -257,7 +267,7 @@ class BatchSolver {
   }
 
  private:
-  b200qp_int batch_, m_, n_;
+  b200qp_int batch_, m_, n_, nnzP_ = 0, nnzA_ = 0;   // nnz of the triu-CSC P and of the CSC A given at setup
   b200qp_batch* b_ = nullptr;
 };
 
@@ -418,6 +428,7 @@ PYBIND11_MODULE(osqp_cuda, mod) {
       .def("solve", &BatchSolver::solve)
       .def("update_data_vec", &BatchSolver::update_data_vec, "q"_a.none(true) = py::none(), "l"_a.none(true) = py::none(),
            "u"_a.none(true) = py::none())
+      .def("update_data_mat", &BatchSolver::update_data_mat, "P_x"_a.none(true) = py::none(), "A_x"_a.none(true) = py::none())
       .def("warm_start", &BatchSolver::warm_start, "x"_a.none(true) = py::none(), "y"_a.none(true) = py::none())
       .def("update_settings", &BatchSolver::update_settings)
       .def("update_rho", &BatchSolver::update_rho)

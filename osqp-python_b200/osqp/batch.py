@@ -33,7 +33,9 @@ class OSQPBatch(OSQP):
         assert v.shape == (self.batch, width), f"Incorrect shape of {name}: {v.shape}, expected {(self.batch, width)}"
         return np.ascontiguousarray(v)
 
-    def setup(self, P, q, A, l, u, batch=None, **settings):
+    def setup(self, P, q, A, l, u, batch=None, Px=None, Ax=None, **settings):
+        """P, A: the shared sparsity pattern (and the values of element 0, which fix the scaling); q (batch, n) or (n,),
+        l / u (batch, m) or (m,).  Px / Ax: optional per-element values, see update()."""
         q = np.asarray(q, dtype=np.float64)
         if batch is None:
             assert q.ndim == 2 or np.ndim(l) == 2 or np.ndim(u) == 2, "give batch= or 2-D q / l / u"
@@ -60,11 +62,23 @@ class OSQPBatch(OSQP):
         self._solver = _reraise(self.ext.OSQPBatchSolver, Pc, qb, Ac, lb, ub, self.batch, m, n, self.settings)
         if "rho" in settings:
             self._solver.update_rho(settings["rho"])
+        if Px is not None or Ax is not None:
+            self.update(Px=Px, Ax=Ax)
 
     def update(self, **kwargs):
-        """q / l / u with a leading batch axis (matrix values are shared and fixed at setup)."""
-        if any(k in kwargs for k in ("Px", "Px_idx", "Ax", "Ax_idx")):
-            raise NotImplementedError("OSQPBatch shares (P, A) across the batch; set up a new batch to change them")
+        """q / l / u and / or Px / Ax with a leading batch axis (reference interface.py:330-368).  Px is
+        (batch, nnz(triu P)), Ax is (batch, nnz(A)), values in the CSC order of the matrices given at setup -- the
+        per-element `P_val` / `A_val` of the reference's batched caller (nn/torch.py:136-140).  Index subsets
+        (Px_idx / Ax_idx) are not supported in a batch."""
+        if "Px_idx" in kwargs or "Ax_idx" in kwargs:
+            raise NotImplementedError("OSQPBatch.update takes full value arrays (no Px_idx / Ax_idx)")
+        Px, Ax = kwargs.get("Px"), kwargs.get("Ax")
+        if Px is not None or Ax is not None:
+            Px = None if Px is None else np.ascontiguousarray(np.broadcast_to(np.asarray(Px, dtype=self._dtype), (self.batch, np.shape(Px)[-1])))
+            Ax = None if Ax is None else np.ascontiguousarray(np.broadcast_to(np.asarray(Ax, dtype=self._dtype), (self.batch, np.shape(Ax)[-1])))
+            rc = _reraise(self._solver.update_data_mat, Px, Ax)
+            if rc:
+                raise OSQPException(rc)
         infty = self.constant("OSQP_INFTY")
         q, l, u = kwargs.get("q"), kwargs.get("l"), kwargs.get("u")
         q = None if q is None else self._batch_array(q, self.n, "q")

@@ -246,3 +246,77 @@ def test_mid_size_batch_falls_back_to_pcg():
         ora = _oracle_element(P, q[0], A, l0, u0, q[b], l0, u0, **kw)
         assert res.info.status[b] == "solved" and ora.info.status == "solved"
         assert _rel(res.x[b], ora.x) < REL and _rel(res.y[b], ora.y) < 10 * REL
+
+
+def _perturbed_matrices(P, A, B, rng):
+    """Per-element values on the shared pattern: P_b = P + diag(nonnegative), A_b = A .* (1 + small)."""
+    Pt = sparse.triu(P, format="csc")
+    Pt.sort_indices()
+    Ac = sparse.csc_matrix(A)
+    Ac.sort_indices()
+    Px = np.tile(Pt.data, (B, 1))
+    rows = Pt.indices
+    cols = np.repeat(np.arange(Pt.shape[1]), np.diff(Pt.indptr))
+    diag = rows == cols
+    Px[:, diag] += 0.5 * rng.random((B, int(diag.sum())))
+    Ax = np.tile(Ac.data, (B, 1)) * (1.0 + 0.02 * rng.standard_normal((B, Ac.nnz)))
+    Px[0], Ax[0] = Pt.data, Ac.data
+    return Pt, Ac, Px, Ax
+
+
+def test_per_element_matrix_values(mode):
+    """Element b = setup(element 0) + update(Px=Px[b], Ax=Ax[b], q=q[b]) + solve(): the reference's cached-solver
+    path for per-element P_val / A_val (src/osqp/nn/torch.py:136-140)."""
+    import osqp
+    from b200qp import problems
+    from oracle.osqp_oracle import OracleSolver
+    B, n, m = 7, 40, 60
+    P, q0, A, l, u = problems.random_qp(n, m, nnz_per_row=4, seed=31, eq_frac=0.0)
+    rng = np.random.default_rng(3)
+    Pt, Ac, Px, Ax = _perturbed_matrices(P, A, B, rng)
+    q = q0 + 0.2 * rng.standard_normal((B, n))
+    q[0] = q0
+    l, u = l - 0.5, u + 0.5                       # keep every perturbed element feasible
+    kw = dict(eps_abs=1e-9, eps_rel=1e-9, max_iter=50000)
+    prob = osqp.OSQPBatch()
+    prob.setup(P, q, A, l, u, Px=Px, Ax=Ax, verbose=False, cg_tol_fraction=1e-3, **kw)
+    res = prob.solve()
+    for b in range(B):
+        s = OracleSolver(P, q0, A, l, u, linsys="direct", **kw)
+        s.update(q=q[b], Px=Px[b], Ax=Ax[b], P_pattern=Pt, A_pattern=Ac)
+        ora = s.solve()
+        assert res.info.status[b] == ora.info.status == "solved", (b, res.info.status[b], ora.info.status)
+        assert _rel(res.x[b], ora.x) < REL and _rel(res.y[b], ora.y) < 10 * REL, (b, _rel(res.x[b], ora.x), _rel(res.y[b], ora.y))
+        assert abs(res.info.obj_val[b] - ora.info.obj_val) <= REL * max(1.0, abs(ora.info.obj_val))
+    # updating only A afterwards keeps the per-element P; back to element 0's A everywhere
+    prob.update(Ax=Ac.data)
+    prob.update_settings(rho=0.1)
+    prob.update_settings(warm_starting=False)
+    res2 = prob.solve()
+    s = OracleSolver(P, q0, A, l, u, linsys="direct", **kw)
+    s.update(q=q[3], Px=Px[3], P_pattern=Pt)
+    ora = s.solve()
+    assert _rel(res2.x[3], ora.x) < REL and abs(res2.info.obj_val[3] - ora.info.obj_val) <= REL * max(1.0, abs(ora.info.obj_val))
+    with pytest.raises(osqp.OSQPException):
+        prob.update(Ax=np.zeros((B, Ac.nnz + 1)))
+
+
+def test_per_element_values_equal_to_shared_give_the_same_solves():
+    """Same numbers through the per-element path (values re-scaled as E a D in one product instead of the ten Ruiz
+    passes of setup: equal up to rounding)."""
+    import osqp
+    from b200qp import problems
+    B = 6
+    P, q, A, l, u = problems.mpc_batch(B)
+    shared = osqp.OSQPBatch()
+    shared.setup(P, q, A, l, u, verbose=False, warm_starting=False)
+    r1 = shared.solve()
+    Pt = sparse.triu(P, format="csc"); Pt.sort_indices()
+    Ac = sparse.csc_matrix(A); Ac.sort_indices()
+    per = osqp.OSQPBatch()
+    per.setup(P, q, A, l, u, Px=np.tile(Pt.data, (B, 1)), Ax=np.tile(Ac.data, (B, 1)), verbose=False, warm_starting=False)
+    r2 = per.solve()
+    np.testing.assert_array_equal(r1.info.iter, r2.info.iter)
+    np.testing.assert_allclose(r2.x, r1.x, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(r2.y, r1.y, rtol=0, atol=1e-9)
+    assert per.stats()["dense"] == 1
