@@ -16,6 +16,9 @@
  *   osqp_cleanup          src/bindings.cpp.in:160           ->  b200qp_cleanup
  *   osqp_set_default_settings  src/bindings.cpp.in:449      ->  b200qp_set_default_settings
  *   osqp_capabilities     src/bindings.cpp.in:402           ->  b200qp_capabilities
+ *   osqp_adjoint_derivative_compute  src/bindings.cpp.in:301  ->  b200qp_adjoint_derivative_compute
+ *   osqp_adjoint_derivative_get_mat  src/bindings.cpp.in:309  ->  b200qp_adjoint_derivative_get_mat
+ *   osqp_adjoint_derivative_get_vec  src/bindings.cpp.in:318  ->  b200qp_adjoint_derivative_get_vec
  *   OSQPCscMatrix / OSQPSettings / OSQPInfo / OSQPSolution / OSQPSolver
  *                         src/bindings.cpp.in:41-48, 405-447, 473-492, 79-105, 163-176
  *
@@ -199,6 +202,18 @@ b200qp_int b200qp_update_data_mat(b200qp_solver *solver, const b200qp_float *Px_
 b200qp_int b200qp_update_settings(b200qp_solver *solver, const b200qp_settings *new_settings);
 b200qp_int b200qp_update_rho(b200qp_solver *solver, b200qp_float rho_new);
 b200qp_int b200qp_get_stats(const b200qp_solver *solver, b200qp_stats *stats);
+
+/* ---- adjoint derivatives of a loss L(x*, y*) (reference: src/osqp/interface.py:519-598,
+ * src/bindings.cpp.in:283-319; semantics pinned by src/osqp/tests/derivative_test.py) -----------------------
+ * After a solve() that ended SOLVED: compute(dx = dL/dx, dy = dL/dy or NULL) solves the adjoint KKT system of the
+ * active set ON DEVICE (the same persistent ADMM kernel, run on the equality-constrained auxiliary QP
+ * min 1/2 r'P r - dx'r  s.t. a_i'r = dy_i on the active rows); get_vec / get_mat then return
+ *   dq = -rx,  dl_i / du_i = ry_i on lower- / upper-active rows,
+ *   dP = -(rx x' + x rx')/2 on the upper-triangular pattern passed in dP,  dA = -(y rx' + ry x') on the pattern in dA
+ * (dP->x and dA->x are overwritten; p and i describe the patterns of the matrices given at setup). */
+b200qp_int b200qp_adjoint_derivative_compute(b200qp_solver *solver, const b200qp_float *dx, const b200qp_float *dy);
+b200qp_int b200qp_adjoint_derivative_get_mat(b200qp_solver *solver, b200qp_csc *dP, b200qp_csc *dA);
+b200qp_int b200qp_adjoint_derivative_get_vec(b200qp_solver *solver, b200qp_float *dq, b200qp_float *dl, b200qp_float *du);
 
 /* ---- multi-GPU: ONE QP row-partitioned over `world` GPUs (BASELINE.json configs[3]) ----
  * Not in the reference (its CUDA algebra is single-GPU: OSQPSettings.device is one int,

@@ -544,3 +544,42 @@ class OracleSolver:
 def solve_qp(P, q, A, l, u, linsys="direct", **kw):
     """One-shot helper."""
     return OracleSolver(P, q, A, l, u, linsys=linsys, **kw).solve()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Adjoint derivatives (reference surface: src/osqp/interface.py:519-598, src/bindings.cpp.in:283-319;
+# semantics pinned by src/osqp/tests/derivative_test.py: gradients of a loss L(x*, y*) with respect to
+# P, q, A, l, u, checked there against finite differences).  The upstream C routine is not vendored; this
+# is the textbook active-set adjoint of the KKT system, used as the checker of the engine's implementation.
+def adjoint_derivative(P, q, A, l, u, x, y, dx, dy=None, z=None):
+    """Given a solution (x, y) and dL/dx (=dx), dL/dy (=dy): returns (dP, dq, dA, dl, du).
+
+    Active rows (polish guess, ref:1719-1720): lower if z - l < -y, upper if u - z < y.  Solve
+        [P  Aa'] [rx]   [dx ]
+        [Aa  0 ] [ry] = [dya]
+    then  dq = -rx,  dP = -(rx x' + x rx')/2 (upper triangle is what the reference compares),
+          dA = -(y rx' + ry x'),  dl_i = ry_i on lower-active rows, du_i = ry_i on upper-active rows.
+    dP, dA are dense arrays."""
+    Pf = full_symmetric(P).toarray() if sp.issparse(P) else np.asarray(P, float)
+    Ad = A.toarray() if sp.issparse(A) else np.asarray(A, float)
+    n, m = len(q), Ad.shape[0]
+    x, y = np.asarray(x, float), np.asarray(y, float)
+    dx = np.asarray(dx, float)
+    dy = np.zeros(m) if dy is None else np.asarray(dy, float)
+    z = Ad @ x if z is None else np.asarray(z, float)
+    low = (z - l) < -y
+    upp = (u - z) < y
+    act = low | upp
+    Aa = Ad[act]
+    k = int(act.sum())
+    K = np.block([[Pf, Aa.T], [Aa, np.zeros((k, k))]])
+    sol = np.linalg.lstsq(K, np.concatenate([dx, dy[act]]), rcond=None)[0]
+    rx = sol[:n]
+    ry = np.zeros(m)
+    ry[act] = sol[n:]
+    dq = -rx
+    dP = -0.5 * (np.outer(rx, x) + np.outer(x, rx))
+    dA = -(np.outer(y, rx) + np.outer(ry, x))
+    dl = np.where(low, ry, 0.0)
+    du = np.where(upp & ~low, ry, 0.0)
+    return dP, dq, dA, dl, du

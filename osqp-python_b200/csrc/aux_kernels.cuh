@@ -256,4 +256,27 @@ __global__ void k_polish_dual(int n, const double* __restrict__ px, const double
   xq[i] = x[i] * (0.5 * px[i] + q[i]);
 }
 
+// ---- adjoint derivatives (reference surface: interface.py:519-598) ---------------------------------------------
+// Auxiliary equality-constrained QP of the adjoint KKT system: active rows (same guess as polish, ref:1719-1720)
+// become equalities a_i'r = dy_i (scaled: E_i dy_i), the others are released; act = 1 lower-active, 2 upper-active.
+__global__ void k_adjoint_prepare(int m, const double* __restrict__ l, const double* __restrict__ u,
+                                  const double* __restrict__ z, const double* __restrict__ y,
+                                  const double* __restrict__ dy, const double* __restrict__ E, double rho_act,
+                                  double* __restrict__ lp, double* __restrict__ up, int* __restrict__ ctp,
+                                  double* __restrict__ rho_v, double* __restrict__ rho_inv, int* __restrict__ act) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double zi = z[i], yi = y[i];
+  const bool low = (zi - l[i]) < -yi, upp = (u[i] - zi) < yi;
+  act[i] = low ? 1 : (upp ? 2 : 0);
+  if (low || upp) {
+    const double b = dy ? E[i] * dy[i] : 0.0;
+    lp[i] = b; up[i] = b; ctp[i] = 1;
+    rho_v[i] = rho_act; rho_inv[i] = 1.0 / rho_act;
+  } else {
+    lp[i] = -QP_INFTY; up[i] = QP_INFTY; ctp[i] = -1;
+    rho_v[i] = RHO_MIN; rho_inv[i] = 1.0 / RHO_MIN;
+  }
+}
+
 }  // namespace b200qp

@@ -132,6 +132,12 @@ struct Work {
   // polish workspace (allocated on first use)
   DBuf<double> pol_l, pol_u, pol_rho, pol_rhoinv, pol_Minv, bk_x, bk_z, bk_y, bk_ax;
   DBuf<int> pol_ctype, pol_count;
+  // adjoint derivatives (allocated on first use): auxiliary q, active-set flags; host copies of rx, ry
+  DBuf<double> adj_q;
+  DBuf<int> adj_act;
+  std::vector<double> h_rx, h_ry;
+  std::vector<int> h_act;
+  bool adj_ready = false;
   DBuf<int> part_n, part_m;
   DBuf<double> red;
   DBuf<Ctrl> ctrl;
@@ -174,7 +180,7 @@ struct Work {
                             &z, &y, &ax, &w2, &w, &rho_v, &rho_inv, &tmp_m, &stage_d, &sol_n, &sol_m, &cert_n, &cert_m,
                             &scal, &red, &red_part, &pol_l, &pol_u, &pol_rho, &pol_rhoinv, &pol_Minv, &bk_x, &bk_z, &bk_y, &bk_ax})
       b->free();
-    pol_ctype.free(); pol_count.free();
+    pol_ctype.free(); pol_count.free(); adj_q.free(); adj_act.free();
     ctype.free(); stage_i.free(); part_n.free(); part_m.free(); ctrl.free(); out.free(); log.free();
     for (int h = 0; h < MAXW; ++h)
       if (dist.opened[h] && dist.peer[h]) cudaIpcCloseMemHandle(dist.peer[h]);
@@ -461,7 +467,7 @@ b200qp_int b200qp_device_count(void) {
 }
 
 b200qp_int b200qp_capabilities(void) {
-  return B200QP_CAPABILITY_INDIRECT_SOLVER | B200QP_CAPABILITY_UPDATE_MATRICES;
+  return B200QP_CAPABILITY_INDIRECT_SOLVER | B200QP_CAPABILITY_UPDATE_MATRICES | B200QP_CAPABILITY_DERIVATIVES;
 }
 
 void b200qp_set_default_settings(b200qp_settings* s) {
@@ -724,6 +730,7 @@ void b200qp_cold_start(b200qp_solver* solver) {
 static b200qp_int solve_begin(b200qp_solver* solver) {
   if (!solver || !solver->work) return B200QP_WORKSPACE_NOT_INIT_ERROR;
   Work* w = W(solver);
+  w->adj_ready = false;
   b200qp_settings* st = solver->settings;
   w->t_solve_begin = now_s();
   try {
@@ -880,6 +887,7 @@ b200qp_int b200qp_update_data_vec(b200qp_solver* solver, const b200qp_float* q_n
   Work* w = W(solver);
   const double t0 = now_s();
   begin_update_timer(solver);
+  w->adj_ready = false;
   try {
     CK(cudaSetDevice(w->device));
     const int n = w->n, m = w->m;
@@ -924,6 +932,7 @@ b200qp_int b200qp_update_data_mat(b200qp_solver* solver, const b200qp_float* Px_
   Work* w = W(solver);
   const double t0 = now_s();
   begin_update_timer(solver);
+  w->adj_ready = false;
   try {
     CK(cudaSetDevice(w->device));
     const int n = w->n;
@@ -1000,6 +1009,152 @@ b200qp_int b200qp_update_settings(b200qp_solver* solver, const b200qp_settings* 
 }
 
 
+
+}  // extern "C"
+
+// ================================================================== adjoint derivatives
+// reference surface: src/osqp/interface.py:519-598, src/bindings.cpp.in:283-319.  The adjoint KKT system
+//   [P Aa'; Aa 0] [rx; ry] = [dx; dy_a]   (Aa = active rows)
+// is the optimality system of  min 1/2 r'P r - dx'r  s.t. Aa r = dy_a, so it is solved by the same persistent ADMM
+// kernel, in the scaled space of the solver (q_aux = -c D dx, bounds E dy on the active rows, the other rows
+// released), exactly the way polish re-uses it; (x, z, y) of the solution are put back afterwards.
+extern "C" b200qp_int b200qp_adjoint_derivative_compute(b200qp_solver* sv, const b200qp_float* dx, const b200qp_float* dy) {
+  if (!sv || !sv->work) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  Work* w = W(sv);
+  b200qp_settings* st = sv->settings;
+  if (w->dist.connected || w->dist.world > 1) return B200QP_FUNC_NOT_IMPLEMENTED;
+  if (!dx || (sv->info->status_val != B200QP_SOLVED && sv->info->status_val != B200QP_SOLVED_INACCURATE)) return B200QP_DATA_NOT_INITIALIZED;
+  const int n = w->n, m = w->m;
+  cudaStream_t s = w->stream;
+  w->adj_ready = false;
+  int rc = 0;
+  try {
+    CK(cudaSetDevice(w->device));
+    if (!w->bk_x.p) {
+      for (DBuf<double>* b : {&w->pol_Minv, &w->bk_x}) b->alloc(n);
+      for (DBuf<double>* b : {&w->pol_l, &w->pol_u, &w->pol_rho, &w->pol_rhoinv, &w->bk_z, &w->bk_y, &w->bk_ax}) b->alloc(m);
+      w->pol_ctype.alloc(m); w->pol_count.alloc(1);
+    }
+    if (!w->adj_q.p) { w->adj_q.alloc(n); w->adj_act.alloc(m); }
+    w->h_rx.assign(n, 0.0); w->h_ry.assign(m, 0.0); w->h_act.assign(m, 0);
+    CK(cudaMemcpyAsync(w->bk_x.p, w->x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (m) {
+      CK(cudaMemcpyAsync(w->bk_z.p, w->z.p, m * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpyAsync(w->bk_y.p, w->y.p, m * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpyAsync(w->bk_ax.p, w->ax.p, m * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    }
+    // auxiliary data: q_aux = -c D dx ; bounds / rho of the active-set equality problem
+    const double* ddx = stage_doubles(w, dx, n, 0);
+    k_vec_set_mul<<<cdiv(n, 256), 256, 0, s>>>(n, w->adj_q.p, ddx, w->D.p, -w->c);
+    if (m) {
+      const double* ddy = dy ? stage_doubles(w, dy, m, n) : nullptr;
+      k_adjoint_prepare<<<cdiv(m, 256), 256, 0, s>>>(m, w->l.p, w->u.p, w->z.p, w->y.p, ddy, w->E.p, 1e3 * st->rho, w->pol_l.p,
+                                                     w->pol_u.p, w->pol_ctype.p, w->pol_rho.p, w->pol_rhoinv.p, w->adj_act.p);
+      CK(cudaMemcpyAsync(w->h_act.data(), w->adj_act.p, m * sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+    k_jacobi<<<cdiv((long long)n * 8, 256), 256, 0, s>>>(w->At.view(), w->pdiag.p, w->pol_rho.p, st->sigma,
+                                                        st->cg_precond == B200QP_DIAGONAL_PRECONDITIONER, w->pol_Minv.p);
+    // cold start of the auxiliary problem
+    w->x.zero(s);
+    if (m) { w->z.zero(s); w->y.zero(s); }
+    double hq[2];
+    launch_absmax_sum(w, n, w->adj_q.p, nullptr, w->scal.p);
+    CK(cudaMemcpyAsync(hq, w->scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const double nq_s = hq[0];
+    launch_absmax_sum(w, n, w->adj_q.p, w->Dinv.p, w->scal.p);
+    CK(cudaMemcpyAsync(hq, w->scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const double nq_t = hq[0];
+
+    KArgs a = make_args(sv);
+    a.q = w->adj_q.p;
+    a.l = w->pol_l.p; a.u = w->pol_u.p; a.ctype = w->pol_ctype.p; a.rho_v = w->pol_rho.p; a.rho_inv = w->pol_rhoinv.p;
+    a.Minv = w->pol_Minv.p;
+    a.nq_s = nq_s; a.nq_t = a.unscale ? nq_t : nq_s;
+    a.polish_mode = 1;
+    a.adaptive_rho = 0;
+    a.verbose = 0;
+    a.check_dualgap = 0;
+    const double base = std::min(st->eps_abs > 0 ? st->eps_abs : st->eps_rel, st->eps_rel > 0 ? st->eps_rel : st->eps_abs);
+    a.eps_abs = a.eps_rel = std::min(1e-8, std::max(1e-13, 1e-2 * base));
+    a.max_iter = 4000;
+    a.check_term = 5;
+    a.cg_max_iter = std::max(4 * st->cg_max_iter, 200);
+    a.cg_tol_frac = std::min(st->cg_tol_fraction, 0.05);
+    a.time_limit_ns = 1e300;
+    const KOut admm = w->h_out;
+    float ms = 0.f;
+    run_admm(sv, a, &ms);
+    const KOut aux = w->h_out;
+    w->h_out = admm;
+    if (aux.aborted || (aux.status != B200QP_SOLVED && aux.status != B200QP_SOLVED_INACCURATE && aux.status != B200QP_MAX_ITER_REACHED))
+      rc = B200QP_LINSYS_SOLVER_INIT_ERROR;
+    else {
+      // rx = D x_aux, ry = E y_aux / c  (same unscaling as a solution)
+      k_store_n<<<cdiv(n, 256), 256, 0, s>>>(n, 0, w->x.p, w->d.p, w->D.p, st->alpha, w->tmp_n.p, w->tmp_n2.p);
+      CK(cudaMemcpyAsync(w->h_rx.data(), w->tmp_n.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+      if (m) {
+        k_store_m<<<cdiv(m, 256), 256, 0, s>>>(m, 0, w->y.p, w->w.p, w->E.p, 1.0 / w->c, w->tmp_m.p, w->cert_m.p);
+        CK(cudaMemcpyAsync(w->h_ry.data(), w->tmp_m.p, m * sizeof(double), cudaMemcpyDeviceToHost, s));
+      }
+      CK(cudaStreamSynchronize(s));
+      for (int i = 0; i < m; ++i) if (!w->h_act[i]) w->h_ry[i] = 0.0;
+      w->adj_ready = true;
+    }
+  } catch (int code) {
+    rc = code;
+  }
+  // the solver's own iterates come back whatever happened
+  cudaMemcpyAsync(w->x.p, w->bk_x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
+  if (m) {
+    cudaMemcpyAsync(w->z.p, w->bk_z.p, m * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(w->y.p, w->bk_y.p, m * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(w->ax.p, w->bk_ax.p, m * sizeof(double), cudaMemcpyDeviceToDevice, s);
+  }
+  cudaStreamSynchronize(s);
+  return rc;
+}
+
+extern "C" b200qp_int b200qp_adjoint_derivative_get_vec(b200qp_solver* sv, b200qp_float* dq, b200qp_float* dl, b200qp_float* du) {
+  if (!sv || !sv->work) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  Work* w = W(sv);
+  if (!w->adj_ready) return B200QP_DATA_NOT_INITIALIZED;
+  if (dq) for (int j = 0; j < w->n; ++j) dq[j] = -w->h_rx[j];
+  for (int i = 0; i < w->m; ++i) {
+    if (dl) dl[i] = w->h_act[i] == 1 ? w->h_ry[i] : 0.0;
+    if (du) du[i] = w->h_act[i] == 2 ? w->h_ry[i] : 0.0;
+  }
+  return 0;
+}
+
+extern "C" b200qp_int b200qp_adjoint_derivative_get_mat(b200qp_solver* sv, b200qp_csc* dP, b200qp_csc* dA) {
+  if (!sv || !sv->work) return B200QP_WORKSPACE_NOT_INIT_ERROR;
+  Work* w = W(sv);
+  if (!w->adj_ready) return B200QP_DATA_NOT_INITIALIZED;
+  const double *x = sv->solution->x, *y = sv->solution->y, *rx = w->h_rx.data(), *ry = w->h_ry.data();
+  if (dP) {
+    if (dP->n != w->n || dP->m != w->n) return B200QP_DATA_VALIDATION_ERROR;
+    for (int j = 0; j < w->n; ++j)
+      for (int k = dP->p[j]; k < dP->p[j + 1]; ++k) {
+        const int i = dP->i[k];
+        if (i < 0 || i >= w->n) return B200QP_DATA_VALIDATION_ERROR;
+        dP->x[k] = -0.5 * (rx[i] * x[j] + x[i] * rx[j]);
+      }
+  }
+  if (dA) {
+    if (dA->n != w->n || dA->m != w->m) return B200QP_DATA_VALIDATION_ERROR;
+    for (int j = 0; j < w->n; ++j)
+      for (int k = dA->p[j]; k < dA->p[j + 1]; ++k) {
+        const int i = dA->i[k];
+        if (i < 0 || i >= w->m) return B200QP_DATA_VALIDATION_ERROR;
+        dA->x[k] = -(y[i] * rx[j] + ry[i] * x[j]);
+      }
+  }
+  return 0;
+}
+
+extern "C" {
 // ================================================================== multi-GPU: one QP, row-partitioned
 // (SURVEY.md 8e config 4).  Every rank receives the full problem, runs the ordinary setup on its own
 // GPU (equilibration needs global column norms anyway), then keeps a row slab of A / A' and joins the

@@ -134,6 +134,27 @@ class Solver {
     return status;
   }
   b200qp_int update_rho(b200qp_float rho) { return b200qp_update_rho(s_, rho); }
+  // adjoint derivatives (reference: src/bindings.cpp.in:283-319)
+  b200qp_int adjoint_derivative_compute(py::object dx, py::object dy) {
+    darray kx, ky;
+    const b200qp_float* px = opt_doubles(dx, kx);
+    const b200qp_float* pyv = opt_doubles(dy, ky);
+    if ((px && kx.size() != n_) || (pyv && ky.size() != m_)) throw py::value_error(std::to_string(B200QP_DATA_VALIDATION_ERROR));
+    py::gil_scoped_release nogil;
+    return b200qp_adjoint_derivative_compute(s_, px, pyv);
+  }
+  b200qp_int adjoint_derivative_get_mat(CscHandle& dP, CscHandle& dA) {
+    // the handles own writable copies of the patterns; their x arrays are overwritten in place
+    dP.view.x = dP.x.mutable_data();
+    dA.view.x = dA.x.mutable_data();
+    return b200qp_adjoint_derivative_get_mat(s_, &dP.view, &dA.view);
+  }
+  b200qp_int adjoint_derivative_get_vec(py::array_t<b200qp_float, py::array::c_style> dq,
+                                        py::array_t<b200qp_float, py::array::c_style> dl,
+                                        py::array_t<b200qp_float, py::array::c_style> du) {
+    if (dq.size() != n_ || dl.size() != m_ || du.size() != m_) throw py::value_error(std::to_string(B200QP_DATA_VALIDATION_ERROR));
+    return b200qp_adjoint_derivative_get_vec(s_, dq.mutable_data(), dl.mutable_data(), du.mutable_data());
+  }
   b200qp_settings* settings() { return s_->settings; }
   b200qp_info* info() { return s_->info; }
   SolutionView& solution() { return sol_; }
@@ -418,6 +439,9 @@ PYBIND11_MODULE(osqp_cuda, mod) {
            "A_i"_a.none(true))
       .def("update_settings", &Solver::update_settings)
       .def("update_rho", &Solver::update_rho)
+      .def("adjoint_derivative_compute", &Solver::adjoint_derivative_compute, "dx"_a.none(true), "dy"_a.none(true))
+      .def("adjoint_derivative_get_mat", &Solver::adjoint_derivative_get_mat, "dP"_a, "dA"_a)
+      .def("adjoint_derivative_get_vec", &Solver::adjoint_derivative_get_vec, "dq"_a.noconvert(), "dl"_a.noconvert(), "du"_a.noconvert())
       .def("get_settings", &Solver::settings, py::return_value_policy::reference_internal)
       .def("get_stats", &Solver::stats);
 

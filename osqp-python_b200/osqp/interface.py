@@ -7,7 +7,8 @@ error behaviour; differences, all deliberate:
 
   * one algebra: 'cuda' (module `osqp_cuda`).  No multi-backend search, and NO CPU fallback:
     if the extension cannot be imported, or no CUDA device exists at setup(), it raises.
-  * codegen and adjoint-derivative methods are absent (capability bits are 0).
+  * codegen is absent (capability bit 0; it emits CPU embedded C).  The adjoint-derivative methods
+    (interface.py:519-598) are provided: the adjoint KKT solve runs on device in the same persistent kernel.
 """
 import importlib
 import os
@@ -123,6 +124,7 @@ class OSQP:
         self._itype = np.int64 if self.ext.OSQP_USE_LONG == 1 else np.int32
         self._solver = None
         self.settings = None
+        self._derivative_cache = {}
 
     raises_error = staticmethod(_reraise)
 
@@ -255,6 +257,8 @@ class OSQP:
         self._solver = _reraise(self.ext.OSQPSolver, Pc, q, Ac, l, u, m, n, self.settings)
         if "rho" in settings:
             self._solver.update_rho(settings["rho"])
+        # problem data as the solver holds it (P upper triangular), for the derivative methods (reference :372)
+        self._derivative_cache = {"P": P.astype(self._dtype), "q": q, "A": A.astype(self._dtype), "l": l, "u": u}
 
     def update(self, **kwargs):
         """q / l / u and/or Px, Px_idx, Ax, Ax_idx (reference interface.py:330-368)."""
@@ -269,6 +273,18 @@ class OSQP:
         if any(k in kwargs for k in ("Px", "Px_idx", "Ax", "Ax_idx")):
             self._solver.update_data_mat(P_x=kwargs.get("Px"), P_i=kwargs.get("Px_idx"),
                                          A_x=kwargs.get("Ax"), A_i=kwargs.get("Ax_idx"))
+        # keep the cached problem data current and forget the last solution (reference :348-368)
+        for name, val in (("q", q), ("l", l), ("u", u)):
+            if val is not None and name in self._derivative_cache:
+                self._derivative_cache[name] = np.asarray(val, dtype=self._dtype)
+        for name, key in (("P", "Px"), ("A", "Ax")):
+            if kwargs.get(key) is not None and name in self._derivative_cache:
+                idx = kwargs.get(key + "_idx")
+                if idx is None:
+                    self._derivative_cache[name].data[:] = kwargs[key]
+                else:
+                    self._derivative_cache[name].data[idx] = kwargs[key]
+        self._derivative_cache.pop("results", None)
 
     def warm_start(self, x=None, y=None):
         return self._solver.warm_start(x, y)
@@ -288,8 +304,10 @@ class OSQP:
             raise OSQPException(info.status_val)
         fields = {k: getattr(info, k) for k in vars(type(info)) if not k.startswith("_")}
         sol = self._solver.solution
-        return SimpleNamespace(x=sol.x, y=sol.y, prim_inf_cert=sol.prim_inf_cert, dual_inf_cert=sol.dual_inf_cert,
-                               info=SimpleNamespace(**fields))
+        results = SimpleNamespace(x=sol.x, y=sol.y, prim_inf_cert=sol.prim_inf_cert, dual_inf_cert=sol.dual_inf_cert,
+                                  info=SimpleNamespace(**fields))
+        self._derivative_cache["results"] = results
+        return results
 
     # engine counters of the last solve (not in the reference; used by bench.py)
     def stats(self):
@@ -299,5 +317,47 @@ class OSQP:
     def codegen(self, *a, **k):
         raise NotImplementedError("codegen is out of scope of the B200 engine (OSQP_CAPABILITY_CODEGEN = 0)")
 
-    def adjoint_derivative_compute(self, *a, **k):
-        raise NotImplementedError("derivatives are out of scope (OSQP_CAPABILITY_DERIVATIVES = 0)")
+    # ------------------------------------------------------------------ adjoint derivatives (reference :519-598)
+    def _solved_results(self):
+        assert self.has_capability("OSQP_CAPABILITY_DERIVATIVES"), "This OSQP object does not support derivatives"
+        try:
+            results = self._derivative_cache["results"]
+        except KeyError:
+            raise ValueError("Problem has not been solved. You cannot take derivatives. Please call the solve function.")
+        if results.info.status_val != SolverStatus.OSQP_SOLVED:
+            raise ValueError("Problem has not been solved to optimality. You cannot take derivatives")
+        return results
+
+    def adjoint_derivative_compute(self, dx=None, dy=None):
+        """Adjoint derivative after solve(): dx = dL/dx, dy = dL/dy (reference interface.py:519-540)."""
+        self._solved_results()
+        dx = np.zeros(self.n) if dx is None else np.ascontiguousarray(dx, dtype=self._dtype)
+        dy = np.zeros(self.m) if dy is None else np.ascontiguousarray(dy, dtype=self._dtype)
+        rc = self._solver.adjoint_derivative_compute(dx, dy)
+        if rc:
+            raise OSQPException(rc)
+
+    def adjoint_derivative_get_mat(self, as_dense=True, dP_as_triu=True):
+        """dP / dA after adjoint_derivative_compute (reference interface.py:542-573)."""
+        self._solved_results()
+        P, A = self._derivative_cache["P"], self._derivative_cache["A"]
+        dPm, dAm = P.copy(), A.copy()
+        rc = self._solver.adjoint_derivative_get_mat(self.ext.CSC(dPm), self.ext.CSC(dAm))
+        if rc:
+            raise OSQPException(rc)
+        if not dP_as_triu:
+            dPm = (dPm + spa.triu(dPm, 1).T).tocsc()
+        if as_dense:
+            return np.array(dPm.todense()), np.array(dAm.todense())
+        return dPm, dAm
+
+    def adjoint_derivative_get_vec(self):
+        """dq / dl / du after adjoint_derivative_compute (reference interface.py:575-598)."""
+        self._solved_results()
+        dq = np.empty(self.n, dtype=self._dtype)
+        dl = np.zeros(self.m, dtype=self._dtype)
+        du = np.zeros(self.m, dtype=self._dtype)
+        rc = self._solver.adjoint_derivative_get_vec(dq, dl, du)
+        if rc:
+            raise OSQPException(rc)
+        return dq, dl, du

@@ -113,3 +113,38 @@ def test_update_rho_pin():
     b = OracleSolver(case["P"], case["q"], case["A"], case["l"], case["u"], **st)
     b.update_rho(0.1)
     assert b.solve().info.iter == a.info.iter
+
+
+def test_oracle_adjoint_derivative_matches_finite_differences():
+    """The checker of the engine's adjoint derivatives (tests/test_gpu_derivative.py) against finite differences of
+    complete oracle solves; problem family of the reference's derivative_test.py:32-47."""
+    import numpy.random as npr
+    from scipy import sparse
+    from scipy.optimize import approx_fprime
+    from oracle.osqp_oracle import adjoint_derivative, solve_qp
+    npr.seed(1)
+    n, m = 8, 5
+    L = npr.randn(n, n - 1)
+    P = sparse.csc_matrix(L.dot(L.T) + 0.1 * sparse.eye(n))
+    x0, s0 = npr.randn(n), npr.rand(m)
+    A = sparse.csc_matrix(npr.randn(m, n))
+    u, l = A.dot(x0) + s0, A.dot(x0) - s0
+    q, tx, ty = npr.randn(n), npr.randn(n), npr.randn(m)
+    kw = dict(eps_abs=1e-10, eps_rel=1e-10, max_iter=200000)
+
+    def loss(P_, q_, A_, l_, u_):
+        r = solve_qp(P_, q_, A_, l_, u_, linsys="direct", **kw)
+        assert r.info.status == "solved"
+        return 0.5 * np.sum((r.x - tx) ** 2) + 0.5 * np.sum((r.y - ty) ** 2), r
+
+    _, r = loss(P, q, A, l, u)
+    dP, dq, dA, dl, du = adjoint_derivative(P, q, A, l, u, r.x, r.y, r.x - tx, r.y - ty)
+    fd = approx_fprime(q, lambda v: loss(P, v, A, l, u)[0], 1e-6)
+    np.testing.assert_allclose(dq, fd, atol=1e-4)
+    fd = approx_fprime(l, lambda v: loss(P, q, A, v, u)[0], 1e-6)
+    np.testing.assert_allclose(dl, fd, atol=1e-4)
+    fd = approx_fprime(u, lambda v: loss(P, q, A, l, v)[0], 1e-6)
+    np.testing.assert_allclose(du, fd, atol=1e-4)
+    Ad = A.toarray()
+    fd = approx_fprime(Ad.ravel(), lambda v: loss(P, q, sparse.csc_matrix(v.reshape(m, n)), l, u)[0], 1e-6).reshape(m, n)
+    np.testing.assert_allclose(dA, fd, atol=1e-3)
