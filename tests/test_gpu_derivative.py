@@ -32,6 +32,13 @@ def get_prob(n=10, m=3, seed=1):                                            # de
     return P, q, A, l, u, npr.randn(n), npr.randn(m)
 
 
+def csc_index(M):
+    """(rows, cols) in the storage order of M.data.  The reference test uses M.nonzero() for this
+    (derivative_test.py:342, 386), which newer scipy returns in row-major order -- not the order of .data."""
+    M = sparse.csc_matrix(M)
+    return M.indices.copy(), np.repeat(np.arange(M.shape[1]), np.diff(M.indptr))
+
+
 def solve(P, q, A, l, u):
     import osqp
     prob = osqp.OSQP(algebra="cuda")
@@ -80,7 +87,7 @@ def test_dl_dq():                                                            # d
 
 def test_dl_dP():                                                            # derivative_test.py:337-379
     P, q, A, l, u, tx, _ = get_prob(3, 3)
-    P_idx = P.nonzero()
+    P_idx = csc_index(P)
     (dP, _, _, _, _), _ = get_grads(P, q, A, l, u, tx)
     f = lambda pv: loss(sparse.csc_matrix((pv, P_idx), shape=P.shape), q, A, l, u, tx)
     dP_fd = sparse.csc_matrix((approx_fprime(P.data, f, GRAD_EPS), P_idx), shape=P.shape)
@@ -90,7 +97,7 @@ def test_dl_dP():                                                            # d
 
 def test_dl_dA():                                                            # derivative_test.py:381-422
     P, q, A, l, u, tx, _ = get_prob(3, 3)
-    A_idx = A.nonzero()
+    A_idx = csc_index(A)
     (_, _, dA, _, _), _ = get_grads(P, q, A, l, u, tx)
     f = lambda av: loss(P, q, sparse.csc_matrix((av, A_idx), shape=A.shape), l, u, tx)
     dA_fd = sparse.csc_matrix((approx_fprime(A.data, f, GRAD_EPS), A_idx), shape=A.shape)
