@@ -240,7 +240,7 @@ b200qp_int b200qp_dist_solve_group(b200qp_solver **group, b200qp_int world);
  * reference user gets from setup(P, q[0], A, l[0], u[0]) followed by update(q=q[b], l=l[b], u=u[b]) and
  * solve() -- same scaling (D, E, c of element 0; update() never re-equilibrates, _osqp.py:1312-1367), own
  * ADMM state and own rho.  q is batch x n, l and u are batch x m, row-major, HOST buffers consumed before
- * the call returns.  Multi-GPU: one b200qp_batch per GPU (settings->device) over a shard of the batch; no
+ * the call returns; bounds beyond +-B200QP_INFTY are clipped on device.  Multi-GPU: one b200qp_batch per GPU (settings->device) over a shard of the batch; no
  * collective.  Polish is not run on batch elements (status_polish stays 0).  Matrix VALUES may also differ per
  * element (b200qp_batch_update_data_mat); the sparsity pattern is shared. */
 typedef struct b200qp_batch b200qp_batch;

@@ -101,6 +101,21 @@ __global__ void kb_update_P(long long total, int nnzPt, int nnzP, int n, const d
   if (posL[k] >= 0) Pv[b * nnzP + posL[k]] = v; else pdv[b * n + i] = v;
 }
 
+// New bounds of a whole batch: clip to +-INFTY (interface.py:237-238), scale by E (_osqp.py:1353), check l <= u
+// against the other bound -- the new one if given, else the stored (already scaled) one -- and raise *bad
+// (reference: _osqp.py:1348, 1388, 1419).  The scaled values stay in the staging buffers until the check passed.
+__global__ void kb_bounds(long long total, int m, double* __restrict__ l_new, double* __restrict__ u_new,
+                          const double* __restrict__ l_cur, const double* __restrict__ u_cur,
+                          const double* __restrict__ E, int* __restrict__ bad) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const double e = E[t % m];
+  double lo = l_cur[t], hi = u_cur[t];
+  if (l_new) { lo = e * fmin(fmax(l_new[t], -QP_INFTY), QP_INFTY); l_new[t] = lo; }
+  if (u_new) { hi = e * fmin(fmax(u_new[t], -QP_INFTY), QP_INFTY); u_new[t] = hi; }
+  if (!(lo <= hi + 1e-12 * fabs(hi))) *bad = 1;
+}
+
 typedef void (*batch_fn)(const BArgs);
 int pick_blg(double avg) { return avg <= 12.0 ? 4 : 16; }
 batch_fn pick_batch_kernel(int lgn, int lgm, bool dense, int nt) {
@@ -185,10 +200,25 @@ void upload_scaled(b200qp_batch* b, const double* h, int len, double* out, const
   kb_scale_rows<<<cdiv(total, 256), 256, 0, b->stream>>>(total, len, out, b->stage, s, scalar);
 }
 
-bool bounds_ok(const double* l, const double* u, long long cnt) {
-  for (long long i = 0; i < cnt; ++i)
-    if (!(l[i] <= u[i])) return false;
-  return true;
+// validate + install new bounds (either may be null); returns 0 or B200QP_DATA_VALIDATION_ERROR, in which case
+// the stored bounds are untouched.  Device-side: no host pass over the batch x m entries.
+int set_bounds(b200qp_batch* b, const double* l_new, const double* u_new) {
+  const long long bm = (long long)b->batch * b->m;
+  if (!bm || (!l_new && !u_new)) return 0;
+  double* sl = l_new ? b->stage : nullptr;
+  double* su = u_new ? b->stage + bm : nullptr;
+  if (l_new) BCK(cudaMemcpyAsync(sl, l_new, bm * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  if (u_new) BCK(cudaMemcpyAsync(su, u_new, bm * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  BCK(cudaMemsetAsync(b->next, 0, sizeof(int), b->stream));        // the work counter doubles as the flag
+  kb_bounds<<<cdiv(bm, 256), 256, 0, b->stream>>>(bm, b->m, sl, su, b->l, b->u, b->v.E, b->next);
+  int bad = 0;
+  BCK(cudaMemcpyAsync(&bad, b->next, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  BCK(cudaStreamSynchronize(b->stream));
+  if (bad) return B200QP_DATA_VALIDATION_ERROR;
+  if (l_new) BCK(cudaMemcpyAsync(b->l, sl, bm * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
+  if (u_new) BCK(cudaMemcpyAsync(b->u, su, bm * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
+  BCK(cudaStreamSynchronize(b->stream));
+  return 0;
 }
 
 }  // namespace
@@ -207,13 +237,15 @@ b200qp_int b200qp_batch_setup(b200qp_batch** batchp, b200qp_int batch, const b20
   *batchp = nullptr;
   const double t0 = now_s();
   if (batch <= 0 || !settings || !q || n <= 0 || m < 0 || (m > 0 && (!l || !u))) return B200QP_DATA_VALIDATION_ERROR;
-  if (m > 0 && !bounds_ok(l, u, (long long)batch * m)) return B200QP_DATA_VALIDATION_ERROR;
   b200qp_batch* b = new b200qp_batch();
   b200qp_settings st = *settings;
   st.verbose = 0;
   st.polishing = 0;
   // element 0 fixes the scaling (the reference's setup(); later elements are update()s of it)
-  int rc = b200qp_setup(&b->proto, P, q, A, l, u, m, n, &st);
+  // element 0, bounds clipped to +-INFTY as the single-solver facade does (interface.py:237-238)
+  std::vector<double> l0(m), u0(m);
+  for (int i = 0; i < m; ++i) { l0[i] = std::min(std::max(l[i], -B200QP_INFTY), B200QP_INFTY); u0[i] = std::min(std::max(u[i], -B200QP_INFTY), B200QP_INFTY); }
+  int rc = b200qp_setup(&b->proto, P, q, A, l0.data(), u0.data(), m, n, &st);
   if (rc) { delete b; return rc; }
   b->proto->settings->verbose = settings->verbose;
   try {
@@ -228,7 +260,7 @@ b200qp_int b200qp_batch_setup(b200qp_batch** batchp, b200qp_int batch, const b20
     b->q = dalloc(bn); b->xs = dalloc(bn); b->sol_x = dalloc(bn); b->cert_n = dalloc(bn);
     b->l = dalloc(bm); b->u = dalloc(bm); b->zs = dalloc(bm); b->ys = dalloc(bm); b->sol_y = dalloc(bm); b->cert_m = dalloc(bm);
     b->rho_b = dalloc(batch);
-    b->stage = dalloc(std::max(bn, bm));
+    b->stage = dalloc(std::max(bn, 2 * bm));
     BCK(cudaMalloc(&b->info, (size_t)batch * sizeof(BInfo)));
     BCK(cudaMalloc(&b->next, sizeof(int)));
     b->h_x = halloc(bn); b->h_y = halloc(bm); b->h_cn = halloc(bn); b->h_cm = halloc(bm);
@@ -244,10 +276,10 @@ b200qp_int b200qp_batch_setup(b200qp_batch** batchp, b200qp_int batch, const b20
     upload_scaled(b, q, n, b->q, b->v.D, b->v.c);                 // q <- c D q   (_osqp.py:1328)
     BCK(cudaStreamSynchronize(b->stream));                        // stage is re-used
     if (m) {
-      upload_scaled(b, l, m, b->l, b->v.E, 1.0);                  // l <- E l     (_osqp.py:1353)
-      BCK(cudaStreamSynchronize(b->stream));
-      upload_scaled(b, u, m, b->u, b->v.E, 1.0);
-      BCK(cudaStreamSynchronize(b->stream));
+      BCK(cudaMemsetAsync(b->l, 0, bm * sizeof(double), b->stream));
+      BCK(cudaMemsetAsync(b->u, 0, bm * sizeof(double), b->stream));
+      rc = set_bounds(b, l, u);                                   // l <- E l, u <- E u, every element l <= u
+      if (rc) throw rc;
     }
     // launch geometry: every vector of one QP in shared memory
     b->lgn = pick_blg(n ? (double)(b->v.P.nnz + b->v.At.nnz) / n / 2 : 1.0);
@@ -366,24 +398,9 @@ b200qp_int b200qp_batch_update_data_vec(b200qp_batch* b, const b200qp_float* q_n
   const double t0 = now_s();
   try {
     BCK(cudaSetDevice(b->device));
-    const long long bm = (long long)b->batch * b->m;
-    if ((l_new || u_new) && bm) {
-      // validate l <= u against the bounds that stay (reference: _osqp.py:1348, 1388, 1419)
-      std::vector<double> cur;
-      if (!l_new || !u_new) {
-        cur.resize(bm);
-        kb_scale_rows<<<cdiv(bm, 256), 256, 0, b->stream>>>(bm, b->m, b->stage, l_new ? b->u : b->l, b->v.Einv, 1.0);
-        BCK(cudaMemcpyAsync(cur.data(), b->stage, bm * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-        BCK(cudaStreamSynchronize(b->stream));
-      }
-      for (long long i = 0; i < bm; ++i) {
-        const double lo = l_new ? l_new[i] : cur[i], hi = u_new ? u_new[i] : cur[i];
-        if (!(lo <= hi + 1e-12 * std::fabs(hi))) return B200QP_DATA_VALIDATION_ERROR;
-      }
-    }
+    const int rcb = set_bounds(b, l_new, u_new);
+    if (rcb) return rcb;
     if (q_new) { upload_scaled(b, q_new, b->n, b->q, b->v.D, b->v.c); BCK(cudaStreamSynchronize(b->stream)); }
-    if (l_new && bm) { upload_scaled(b, l_new, b->m, b->l, b->v.E, 1.0); BCK(cudaStreamSynchronize(b->stream)); }
-    if (u_new && bm) { upload_scaled(b, u_new, b->m, b->u, b->v.E, 1.0); BCK(cudaStreamSynchronize(b->stream)); }
     for (int i = 0; i < b->batch; ++i) b->h_info[i].status = B200QP_UNSOLVED;
   } catch (int code) {
     return code;

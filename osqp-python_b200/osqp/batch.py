@@ -44,12 +44,11 @@ class OSQPBatch(OSQP):
         first = lambda v: None if v is None else (np.asarray(v)[0] if np.ndim(v) == 2 else np.asarray(v))
         m, n, Pn, _, An, _, _ = self._infer_mnpqalu(P=P, q=first(q), A=A, l=first(l), u=first(u))
         self.m, self.n = m, n
-        infty = self.constant("OSQP_INFTY")
         if m:
             l = np.full(m, -np.inf) if l is None else l
             u = np.full(m, np.inf) if u is None else u
-            lb = np.maximum(self._batch_array(l, m, "l"), -infty)
-            ub = np.minimum(self._batch_array(u, m, "u"), infty)
+            lb = self._batch_array(l, m, "l")                                  # clipped to +-OSQP_INFTY on device
+            ub = self._batch_array(u, m, "u")
         else:
             lb = ub = np.zeros((self.batch, 0))
         qb = self._batch_array(q, n, "q")
@@ -79,11 +78,10 @@ class OSQPBatch(OSQP):
             rc = _reraise(self._solver.update_data_mat, Px, Ax)
             if rc:
                 raise OSQPException(rc)
-        infty = self.constant("OSQP_INFTY")
         q, l, u = kwargs.get("q"), kwargs.get("l"), kwargs.get("u")
         q = None if q is None else self._batch_array(q, self.n, "q")
-        l = None if l is None else np.maximum(self._batch_array(l, self.m, "l"), -infty)
-        u = None if u is None else np.minimum(self._batch_array(u, self.m, "u"), infty)
+        l = None if l is None else self._batch_array(l, self.m, "l")      # clipped to +-OSQP_INFTY on device
+        u = None if u is None else self._batch_array(u, self.m, "u")
         if q is not None or l is not None or u is not None:
             rc = self._solver.update_data_vec(q=q, l=l, u=u)
             if rc:

@@ -320,3 +320,36 @@ def test_per_element_values_equal_to_shared_give_the_same_solves():
     np.testing.assert_allclose(r2.x, r1.x, rtol=0, atol=1e-9)
     np.testing.assert_allclose(r2.y, r1.y, rtol=0, atol=1e-9)
     assert per.stats()["dense"] == 1
+
+
+def test_unconstrained_and_tiny_batches(mode):
+    """m = 0 (reference unconstrained_test.py) and n = 1..3: x* = -P^-1 q for every element."""
+    import osqp
+    rng = np.random.default_rng(12)
+    for n in (1, 3, 30):
+        M = rng.standard_normal((n, n))
+        P = sparse.csc_matrix(M @ M.T + np.eye(n))
+        B = 5
+        q = rng.standard_normal((B, n))
+        prob = osqp.OSQPBatch()
+        prob.setup(P, q, None, None, None, batch=B, verbose=False, eps_abs=1e-9, eps_rel=1e-9)
+        res = prob.solve()
+        assert all(s == "solved" for s in res.info.status)
+        want = -np.linalg.solve(P.toarray(), q.T).T
+        np.testing.assert_allclose(res.x, want, rtol=0, atol=1e-6 * max(1.0, np.abs(want).max()))
+        assert res.y.shape == (B, 0)
+
+
+def test_non_convex_element_is_reported(mode):
+    """Indefinite P: the reference's indirect path must end NON_CVX or MAX_ITER_REACHED (non_convex_test.py:22-56);
+    a convex neighbour in the same batch is not possible (P is shared), so the whole batch reports it."""
+    import osqp
+    P = sparse.diags([1.0, -1.0], format="csc")
+    A = sparse.eye(2, format="csc")
+    q = np.array([[0.1, 0.2], [-0.3, 0.1]])
+    prob = osqp.OSQPBatch()
+    prob.setup(P, q, A, -np.ones(2), np.ones(2), batch=2, verbose=False, max_iter=200)
+    res = prob.solve()
+    assert all(int(s) in (7, 9) for s in res.info.status_val), res.info.status
+    if np.all(res.info.status_val == 9):
+        assert np.all(np.isnan(res.x)) and np.all(np.isnan(res.info.obj_val))
