@@ -106,6 +106,63 @@ class Settings:
     rho_eq_factor: float = 1e3
 
 
+# ---- optional multi-threaded SpMV for the engine-spec mode (oracle/spmv_omp.c, built by build.py) --------------
+_OMP = None
+
+
+def _omp_lib():
+    """ctypes handle of oracle/_build/liboracle_spmv.so, or False when it was not built."""
+    global _OMP
+    if _OMP is None:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "liboracle_spmv.so")
+        try:
+            lib = ctypes.CDLL(path)
+            lib.oracle_csr_matvec.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 5
+            lib.oracle_csr_matvec.restype = None
+            lib.oracle_omp_threads.restype = ctypes.c_int
+            _OMP = lib
+        except OSError:
+            _OMP = False
+    return _OMP
+
+
+_OMP_WINS = None      # decided by timing both paths once on the first large product
+
+
+def host_threads():
+    """Threads the oracle's large SpMVs run on: the OpenMP helper's, if it is present AND measured faster than
+    scipy's single-threaded csr_matvec on this host (containers with a CPU quota see no gain); else 1."""
+    lib = _omp_lib()
+    return int(lib.oracle_omp_threads()) if (lib and _OMP_WINS) else 1
+
+
+def _matvec_omp(lib, M, v):
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    out = np.empty(M.shape[0])
+    lib.oracle_csr_matvec(M.shape[0], M.indptr.ctypes.data, M.indices.ctypes.data, M.data.ctypes.data,
+                          v.ctypes.data, out.ctypes.data)
+    return out
+
+
+def _matvec(M, v):
+    """M @ v for CSR M; large products go through the OpenMP helper when it is available and faster."""
+    global _OMP_WINS
+    lib = _omp_lib()
+    if not lib or M.nnz < 200_000 or M.indices.dtype != np.int32 or M.indptr.dtype != np.int32:
+        return M @ v
+    if _OMP_WINS is None:
+        t = []
+        for fn in (lambda: _matvec_omp(lib, M, v), lambda: M @ v):
+            fn()
+            t0 = time.perf_counter()
+            fn(); fn()
+            t.append(time.perf_counter() - t0)
+        _OMP_WINS = t[0] < 0.8 * t[1]
+    return _matvec_omp(lib, M, v) if _OMP_WINS else M @ v
+
+
 def _limit(v):
     """ref:363-387: norms below MIN_SCALING -> 1, above MAX_SCALING -> MAX_SCALING."""
     v = np.asarray(v, dtype=float)
@@ -280,10 +337,10 @@ class OracleSolver:
             return xt, zt
         # ---- engine spec: residual-correction PCG on K = P + sigma I + A' rho A
         # r0 = rhs - K x = -(P x + q) + A'(rho (z - A x) - y);  solve K d = r0, xt = x + d
-        ax = self.A @ self.x
-        r = -(self.P @ self.x + self.q)
+        ax = _matvec(self.A, self.x)
+        r = -(_matvec(self.P, self.x) + self.q)
         if self.m:
-            r = r + self.At @ (self.rho_vec * (self.z - ax) - self.y)
+            r = r + _matvec(self.At, self.rho_vec * (self.z - ax) - self.y)
         d = np.zeros(self.n)
         r0n = np.max(np.abs(r)) if self.n else 0.0
         tol = s.cg_tol_fraction * r0n
@@ -292,9 +349,9 @@ class OracleSolver:
             p = zc.copy()
             rz = float(r @ zc)
             for _ in range(int(s.cg_max_iter)):
-                kp = self.P @ p + s.sigma * p
+                kp = _matvec(self.P, p) + s.sigma * p
                 if self.m:
-                    kp = kp + self.At @ (self.rho_vec * (self.A @ p))
+                    kp = kp + _matvec(self.At, self.rho_vec * _matvec(self.A, p))
                 pkp = float(p @ kp)
                 if not (pkp > 0.0):
                     self._cg_breakdown = True
@@ -310,7 +367,7 @@ class OracleSolver:
                 p = zc + (rz_new / rz) * p
                 rz = rz_new
         xt = self.x + d
-        return xt, self.A @ xt
+        return xt, _matvec(self.A, xt)
 
     # ---------------------------------------------------------------- residuals
     def _residuals(self, x, z, y):

@@ -88,6 +88,14 @@ def build(force=False, verbose_ptxas=False):
     if procs or force or _stale(LIB, cu_sources):
         _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs)
         _stamp(LIB, cu_sources)
+    # the oracle's C helper (test infrastructure: OpenMP CSR SpMV for the CPU baseline); building the checker is
+    # not using it
+    osrc = os.path.join(ROOT, "oracle", "spmv_omp.c")
+    olib = os.path.join(ROOT, "oracle", "_build", "liboracle_spmv.so")
+    if os.path.exists(osrc) and (force or _stale(olib, [osrc])):
+        os.makedirs(os.path.dirname(olib), exist_ok=True)
+        _run(["gcc", "-O3", "-fopenmp", "-fPIC", "-shared", "-o", olib, osrc])
+        _stamp(olib, [osrc])
     bind_src = os.path.join(CSRC, "bindings.cpp")
     ext_sources = [bind_src, os.path.join(ROOT, "include", "b200qp.h")]
     if force or _stale(EXT, ext_sources):
