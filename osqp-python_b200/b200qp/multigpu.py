@@ -184,10 +184,10 @@ def bench(args, rank, world, local, B):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": B.workload_name(), "admm_iters_per_step": iters // args.steps,
                        "pcg_iters_per_admm_iter": cg / max(iters, 1), "status": res.info.status,
-                       "partition": f"{world} row slabs of A (balanced by nnz), n-vectors replicated; partial A_g'w "
-                                    "reduced over NVLink inside the persistent kernel (fused reduce-scatter + all-gather)",
-                       "phase_ms_per_step_rank0": dict(zip(["R", "C1_Ap", "C2b_reduce_Kp_push", "C3_axpy_dots", "C4_p", "Z",
-                                                            "C2a_partial_AtW", "x7"], [round(v / args.steps, 3) for v in phases])),
+                       "partition": f"{world} row slabs of A + {world} variable slices of P and A'; p, d, w, w2 all-gathered by "
+                                    "NVLink stores fused into the producing phases of the persistent kernel, x replicated",
+                       "phase_ms_per_step_rank0": dict(zip(["R_slice_push_p", "C1_Ap_push_w", "C2_Kp_slice", "C3_slice_dots", "C4_push_p", "Z_push_w2",
+                                                            "gather_d", "x7"], [round(v / args.steps, 3) for v in phases])),
                        "l2": "inputs larger than L2; no flush between steps", "grid": f"{st['grid']}x{st['block']} per GPU",
                        "setup_s": t_setup, "settings": dict(B.SOLVE_KW)},
             "roofline": {"bound": "hbm", "kernel": "b200qp::admm_kernel_dist (persistent, one launch per rank per solve)",

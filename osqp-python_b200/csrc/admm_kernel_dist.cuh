@@ -1,21 +1,21 @@
-// admm_kernel_dist.cuh -- the persistent ADMM kernel for ONE QP row-partitioned over several GPUs.
+// admm_kernel_dist.cuh -- the persistent ADMM kernel for ONE QP partitioned over several GPUs.
 //
-// Partition: rank g owns a contiguous slab of constraint rows (A_g, z, y, l, u, rho,
-// A x slab) and a slice of the variable space for the reduce step; the n-vectors (x, d, r, p, Kp,
-// Minv) are replicated.  Each rank runs this kernel as its own cooperative launch; ranks meet at
-// cross-GPU barriers built on flags in peer-mapped memory (NVLink / NVSwitch), no host in the loop.
+// Partition.  Rank g owns
+//   * a contiguous slab of constraint rows: A_g, and z, y, l, u, rho, A x on those rows          (m-side work)
+//   * a contiguous slice of the variables: the rows of P and of A' in that slice, and r, Kp, M^-1 (n-side work)
+// so every SpMV and every vector pass shrinks with the number of GPUs.  What each rank needs in full is what the
+// other side gathers from: p and d (n-vectors, gathered by A_g rows) and w, w2, y (m-vectors, gathered by A'
+// rows).  Those five vectors live in a peer-mapped region; a rank writes its own slab / slice locally and PUSHES it
+// into every peer's copy with st.relaxed.sys over NVLink / NVSwitch right where it is produced (all-gather by
+// stores, fused into the producing phase -- no NCCL call, no extra launch, no host in the loop); x is kept
+// replicated by applying the same update from the same d on every rank.  Ranks meet at cross-GPU barriers built on
+// flags in peer-mapped memory; the barrier carries the scalar partials (dots, norms) as payload, folded in rank
+// order, so all ranks see identical bits and take identical control decisions.
 //
-// The one exchange step of the path -- "sum over ranks of A_g' w_g" -- is fused into the kernels
-// that produce and consume it (no NCCL call, no extra launch):
-//     a) every rank writes its partial n-vector A_g' w_g into its own memory             (SpMV)
-//     b) cross-GPU barrier
-//     c) rank g reads slice g of every rank's partial over NVLink in rank order, adds its P-rows
-//        and sigma, forms Kp (or r, p), the dot-product partial, and pushes the finished slice
-//        into every rank's copy                                                          (reduce-scatter
-//        + compute + all-gather in one phase)
-//     d) cross-GPU barrier carrying the scalar partials (dots / norms) as payload
-// Summation order over ranks is fixed and every rank receives the same bits, so all ranks take
-// identical control decisions.  Everything else (C1, C3, C4, Z) is rank-local.
+// Per PCG iteration: C1 (A_g p -> push w) | C2 (slice rows: P p + sigma p + A' w, <p,Kp>) | C3 (slice: d, r, dots)
+// | C4 (slice: p -> push p): four cross-GPU barriers, 2 x 8 (G-1)/G MB pushed per rank, no replicated work.
+// (The first version reduce-scattered partial A_g' w products of full length n: every rank walked all n rows of a
+// matrix with 10/G entries per row and repeated the C3 / C4 passes -- it stopped scaling at 2 GPUs, profiles/r1d.)
 #pragma once
 #include "admm_kernel.cuh"
 
@@ -26,21 +26,22 @@ constexpr int MAXW = 8;
 struct XArgs {
   int rank, world;
   int slice[MAXW + 1];              // variable-space slice boundaries
+  int mlo, mtot;                    // first row of my slab, total number of constraint rows
   // peer-mapped tables: entry h points into rank h's shared region
-  double* part_w[MAXW];             // partial n-vector #1
-  double* part_y[MAXW];             // partial n-vector #2 (A'y on check iterations, Jacobi sums)
-  double* r[MAXW];
-  double* p[MAXW];
-  double* kp[MAXW];
-  double* Minv[MAXW];
+  double* wf[MAXW];                 // full m-vector w  (rho .* A p; the projected delta_y on check iterations)
+  double* w2f[MAXW];                // full m-vector w2 (rho (z - A x) - y)
+  double* yf[MAXW];                 // full m-vector y  (refreshed on check iterations only)
+  double* p[MAXW];                  // full n-vector p
+  double* d[MAXW];                  // full n-vector d
   unsigned long long* flags[MAXW];  // rank h's arrival counters, one per source rank
   double* payload[MAXW];            // rank h's payload area [2][MAXW][KMAX]
   int* abort_flag[MAXW];
-  // local scratch
-  double* sum_w; double* sum_y;     // reduced partials for my slice (full-length buffers, slice used)
+  // local
   double* xtot;                     // [2][KMAX] totals published by CTA 0 to the other CTAs
   unsigned long long* release;      // local release counter of the cross-GPU barrier
-  const int *part_nfull, *part_slice, *part_uni;   // CTA partitions: A_g' rows, my slice by P, uniform n
+  const int *part_slice, *part_uni, *part_mall;   // CTA partitions: my slice (cost of P + A' rows), uniform [0,n), uniform [0,mtot)
+  const int* ctype_full;            // full-length typing / rho vectors: every rank re-derives all of rho at a rho update
+  double *rho_full, *rho_inv_full;
   unsigned long long xepoch0;       // cross-GPU barriers completed by earlier launches (flags are never reset)
 };
 
@@ -179,11 +180,11 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
   __shared__ int s_ok;
 
   const int G = a.G, cta = blockIdx.x, tid = threadIdx.x;
-  const int rank = x.rank, world = x.world;
-  const int f0 = x.part_nfull[cta], f1 = x.part_nfull[cta + 1];     // rows of A_g' handled by this CTA
-  const int s0 = x.part_slice[cta], s1 = x.part_slice[cta + 1];     // my share of this rank's slice
-  const int u0 = x.part_uni[cta], u1 = x.part_uni[cta + 1];         // uniform share of [0, n) (replicated work)
-  const int m0 = a.part_m[cta], m1 = a.part_m[cta + 1];
+  const int rank = x.rank, world = x.world, mlo = x.mlo;
+  const int s0 = x.part_slice[cta], s1 = x.part_slice[cta + 1];     // my share of this rank's variable slice
+  const int u0 = x.part_uni[cta], u1 = x.part_uni[cta + 1];         // uniform share of [0, n) (replicated x)
+  const int g0 = x.part_mall[cta], g1 = x.part_mall[cta + 1];       // uniform share of [0, mtot) (rho re-typing)
+  const int m0 = a.part_m[cta], m1 = a.part_m[cta + 1];             // my share of this rank's row slab (local rows)
   GridSync sync{a.ctrl, G, 0ULL, &s_ok};
   DistSync xs{&sync, &x, x.xepoch0};
   const double NEG_INF = __longlong_as_double(0xfff0000000000000LL);
@@ -200,8 +201,10 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
   const double* Einv_t = a.unscale ? a.Einv : nullptr;
   const double* E_t = a.unscale ? a.E : nullptr;
 
-  double* my_part_w = x.part_w[rank];
-  double* my_part_y = x.part_y[rank];
+  // my copies of the gathered vectors (full length); a.w / a.w2 / a.y are the slab views, a.p / a.d the full ones
+  double* const wfull = x.wf[rank];
+  double* const w2full = x.w2f[rank];
+  double* const yfull = x.yf[rank];
 
   double rho = a.rho;
   int rho_updates = 0, status = 0, k = 0;
@@ -218,45 +221,29 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
 
   auto bank = [&]() -> double* { return a.red + (size_t)(sync.epoch & 1ULL) * KMAX * G; };
 
-  // coalesced reduce-scatter pre-pass for this CTA's rows of the slice: sum over ranks, rank order
-  auto gather_partials = [&](bool second) {
-    for (int i = s0 + tid; i < s1; i += NT) {
-      // all peer loads first (NVLink round trips overlap), then the sum in rank order
-      double vw[MAXW], vy[MAXW];
-#pragma unroll
-      for (int h = 0; h < MAXW; ++h) {
-        vw[h] = (h < world) ? ld_peer(x.part_w[h] + i) : 0.0;
-        vy[h] = (second && h < world) ? ld_peer(x.part_y[h] + i) : 0.0;
-      }
-      double acc = vw[0], acy = vy[0];
-#pragma unroll
-      for (int h = 1; h < MAXW; ++h) if (h < world) { acc += vw[h]; acy += vy[h]; }
-      x.sum_w[i] = acc;
-      if (second) x.sum_y[i] = acy;
-    }
-    __syncthreads();
-  };
-  // push this CTA's finished rows of a replicated vector to every other rank (all-gather by stores)
-  auto push_rows = [&](double* const* table, const double* local) {
-    for (int i = s0 + tid; i < s1; i += NT) {
-      const double v = __ldcg(local + i);
+  // all-gather by stores: push this CTA's rows [lo, hi) (global indices) of my copy into every peer's copy
+  auto push_rows = [&](double* const* table, const double* mine, int lo, int hi) {
+    for (int i = lo + tid; i < hi; i += NT) {
+      const double v = __ldcg(mine + i);
 #pragma unroll
       for (int h = 0; h < MAXW; ++h)
         if (h < world && h != rank) st_sys_f64(table[h] + i, v);
     }
   };
 
-  // ------------------------------------------------------------------ init: ax = A_g x, w2
+  // ------------------------------------------------------------------ init: ax = A_g x, w2 (slab) -> everybody
   for (int base = m0; base < m1; base += NGM) {
     const int row = base + grp_m;
     const bool valid = row < m1;
     const double acc = group_sum<LGM>(row_dot<LGM>(a.A, a.x, row, valid, lane_m));
     if (valid && lane_m == 0) {
       a.ax[row] = acc;
-      a.w2[row] = a.rho_v[row] * (a.z[row] - acc) - a.y[row];
+      a.w2[row] = __ldcg(a.rho_v + row) * (a.z[row] - acc) - a.y[row];
     }
   }
-  B200QP_BARRIER_OR_DIE();
+  __syncthreads();
+  push_rows(x.w2f, w2full, mlo + m0, mlo + m1);
+  B200QP_XBAR_OR_DIE(0, nullptr, 0u);
 
   __shared__ long long t_phase[8];
   __shared__ unsigned long long t_mark;
@@ -265,52 +252,45 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
     if (cta == 0 && tid == 0) { const unsigned long long now = global_timer_ns(); t_phase[id] += (long long)(now - t_mark); t_mark = now; }
   };
 
-  // ---- R phase, distributed: partial A_g' w2 (and A_g' y) -> reduce over ranks -> r, p everywhere
+  // ---- R phase on my slice: r = -(P x + q) + A' w2, p = M^-1 r (pushed); full = also the dual-side quantities;
+  // lite = after a rho update (px kept, Jacobi diagonal from the full rho vector)
   auto phase_R = [&](bool full, bool lite) -> bool {
-    // R1: partials over all n rows of A_g'
-    for (int base = f0; base < f1; base += NGN) {
-      const int row = base + grp_n;
-      const bool valid = row < f1;
-      double atw = 0, sec = 0;
-      if (full) row_dot2<LGN>(a.At, a.w2, a.y, row, valid, lane_n, atw, sec);
-      else {
-        atw = row_dot<LGN>(a.At, a.w2, row, valid, lane_n);
-        if (lite && a.cg_precond) sec = row_dot_sq<LGN>(a.At, a.rho_v, row, valid, lane_n);
-      }
-      atw = group_sum<LGN>(atw);
-      sec = group_sum<LGN>(sec);
-      if (valid && lane_n == 0) {
-        my_part_w[row] = atw;
-        if (full || lite) my_part_y[row] = sec;
-      }
-    }
-    if (!xs.template barrier_x<0>(nullptr, 0u, s_tot)) return false;
-    // R2: my slice
-    gather_partials(full || lite);
     double v[R_K];
 #pragma unroll
     for (int i = 0; i < R_K; ++i) v[i] = 0.0;
     for (int base = s0; base < s1; base += NGN) {
       const int row = base + grp_n;
       const bool valid = row < s1;
-      double px = 0;
-      if (!lite) px = group_sum<LGN>(row_dot<LGN>(a.P, a.x, row, valid, lane_n));
+      double px = 0, atw = 0, aty = 0, msum = 0;
+      if (lite) {
+        atw = row_dot<LGN>(a.At, w2full, row, valid, lane_n);
+        if (a.cg_precond) msum = row_dot_sq<LGN>(a.At, x.rho_full, row, valid, lane_n);
+        msum = group_sum<LGN>(msum);
+      } else {
+        if (full) {
+          px = row_dot<LGN>(a.P, a.x, row, valid, lane_n);
+          row_dot2<LGN>(a.At, w2full, yfull, row, valid, lane_n, atw, aty);
+        } else {
+          dot_pair<LGN, 1, 4>(a.P, a.x, row, valid, a.At, w2full, row, valid, lane_n, px, atw);
+        }
+        px = group_sum<LGN>(px);
+        if (full) aty = group_sum<LGN>(aty);
+      }
+      atw = group_sum<LGN>(atw);
       if (valid && lane_n == 0) {
         const double qj = a.q[row];
         if (lite) {
           px = a.px[row];
-          if (a.cg_precond) a.Minv[row] = 1.0 / (a.pdiag[row] + sigma + __ldcg(x.sum_y + row));
+          if (a.cg_precond) a.Minv[row] = 1.0 / (a.pdiag[row] + sigma + msum);
         }
-        const double atw = __ldcg(x.sum_w + row);
         const double rj = -(px + qj) + atw;
-        const double pj = __ldcg(a.Minv + row) * rj;
+        const double pj = a.Minv[row] * rj;
         a.r[row] = rj;
         a.p[row] = pj;
         v[R_RZ] += rj * pj;
         v[R_R0] = nanmax(v[R_R0], fabs(rj));
         if (full) {
           a.px[row] = px;
-          const double aty = __ldcg(x.sum_y + row);
           const double xj = __ldcg(a.x + row), dj = alpha * __ldcg(a.d + row);
           const double dres = px + qj + aty;
           const double di = Dinv_t ? Dinv_t[row] : 1.0;
@@ -330,9 +310,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
     if (full && tid == 0)
       v[R_TL] = ((double)(global_timer_ns() - t_start) > a.time_limit_ns) ? 1.0 : 0.0;
     __syncthreads();
-    push_rows(x.r, a.r);
-    push_rows(x.p, a.p);
-    if (lite && a.cg_precond) push_rows(x.Minv, a.Minv);
+    push_rows(x.p, a.p, s0, s1);
     double* bk = bank();
     block_reduce_store<R_K>(v, R_MAXMASK, bk, G, s_red);
     if (!xs.template barrier_x<R_K>(bk, R_MAXMASK, s_tot)) return false;
@@ -355,30 +333,13 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
     return true;
   };
 
-  // |Dinv .* scale .* (A' vec)|inf (vec is an m-slab vector) or |Dinv .* scale .* (P vec)|inf
-  auto cert_norm_At = [&](const double* vec, bool& ok) -> double {
-    for (int base = f0; base < f1; base += NGN) {
-      const int row = base + grp_n;
-      const bool valid = row < f1;
-      const double acc = group_sum<LGN>(row_dot<LGN>(a.At, vec, row, valid, lane_n));
-      if (valid && lane_n == 0) my_part_w[row] = acc;
-    }
-    ok = xs.template barrier_x<0>(nullptr, 0u, s_tot);
-    if (!ok) return 0.0;
-    gather_partials(false);
-    double v[1] = {0.0};
-    for (int i = s0 + tid; i < s1; i += NT) v[0] = nanmax(v[0], fabs((Dinv_t ? Dinv_t[i] : 1.0) * __ldcg(x.sum_w + i)));
-    double* bk = bank();
-    block_reduce_store<1>(v, 1u, bk, G, s_red);
-    ok = xs.template barrier_x<1>(bk, 1u, s_tot);
-    return ok ? s_tot[0] : 0.0;
-  };
-  auto cert_norm_P = [&](const double* vec, double scale, bool& ok) -> double {
+  // |Dinv .* scale .* (M vec)|inf over my slice rows, max over ranks (infeasibility certificates)
+  auto cert_norm = [&](const CsrMat& M, const double* vec, double scale, bool& ok) -> double {
     double v[1] = {0.0};
     for (int base = s0; base < s1; base += NGN) {
       const int row = base + grp_n;
       const bool valid = row < s1;
-      const double acc = group_sum<LGN>(row_dot<LGN>(a.P, vec, row, valid, lane_n));
+      const double acc = group_sum<LGN>(row_dot<LGN>(M, vec, row, valid, lane_n));
       if (valid && lane_n == 0) v[0] = nanmax(v[0], fabs((Dinv_t ? Dinv_t[row] : 1.0) * scale * acc));
     }
     double* bk = bank();
@@ -391,7 +352,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
     ok = true;
     if (!(prim_res <= QP_INFTY) || !(dual_res <= QP_INFTY)) return 9;
     const double ea = f * a.eps_abs, er = f * a.eps_rel;
-    const bool prim_ok = (a.m == 0 && world == 1) ? true : (prim_res < ea + er * nprim);
+    const bool prim_ok = (x.mtot == 0) ? true : (prim_res < ea + er * nprim);
     const bool dual_ok = dual_res < ea + er * ndual;
     const bool gap_ok = !a.check_dualgap || (fabs(gap) < ea + er * fmax(fabs(obj), fabs(dobj)));
     if (prim_ok && dual_ok && gap_ok) return f > 1.0 ? 2 : 1;
@@ -399,7 +360,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
     if (!prim_ok) {
       const double eps = f * a.eps_pinf;
       if (ndy > eps && lhs < -eps * ndy) {
-        const double nat = cert_norm_At(a.w, ok);
+        const double nat = cert_norm(a.At, wfull, 1.0, ok);     // w holds the projected delta_y (pushed by the Z phase)
         if (!ok) return 0;
         if (nat < eps * ndy) return f > 1.0 ? 4 : 3;
       }
@@ -407,7 +368,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
     if (!dual_ok) {
       const double eps = f * a.eps_dinf;
       if (ndx > eps && qdx < -c_eff * eps * ndx && vu <= eps * ndx && vl <= eps * ndx) {
-        const double npd = cert_norm_P(a.d, alpha, ok);
+        const double npd = cert_norm(a.P, a.d, alpha, ok);
         if (!ok) return 0;
         if (npd < c_eff * eps * ndx) return f > 1.0 ? 6 : 5;
       }
@@ -454,13 +415,18 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
       if (rho_new > a.adapt_tol * rho || rho_new < rho / a.adapt_tol) {
         rho = rho_new;
         rho_updates++;
-        for (int i = m0 + tid; i < m1; i += NT) {
-          const double rv = rho_of_type(a.ctype[i], rho, a.rho_is_vec, a.rho_eq_factor);
-          a.rho_v[i] = rv;
-          a.rho_inv[i] = 1.0 / rv;
-          a.w2[i] = rv * (a.z[i] - a.ax[i]) - a.y[i];
+        // every rank re-derives the whole rho vector (the A' rows of its slice read all of it), ...
+        for (int i = g0 + tid; i < g1; i += NT) {
+          const double rv = rho_of_type(x.ctype_full[i], rho, a.rho_is_vec, a.rho_eq_factor);
+          x.rho_full[i] = rv;
+          x.rho_inv_full[i] = 1.0 / rv;
         }
         B200QP_BARRIER_OR_DIE();
+        // ... refreshes w2 on its own rows and pushes it
+        for (int i = m0 + tid; i < m1; i += NT) a.w2[i] = __ldcg(a.rho_v + i) * (a.z[i] - a.ax[i]) - a.y[i];
+        __syncthreads();
+        push_rows(x.w2f, w2full, mlo + m0, mlo + m1);
+        B200QP_XBAR_OR_DIE(0, nullptr, 0u);
         if (!phase_R(false, true)) B200QP_DIE();
       }
     }
@@ -470,52 +436,38 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
     if (r0max > 1e-150) {
       const double tol = a.cg_tol_frac * r0max;
       for (int j = 0; j < a.cg_max_iter; ++j) {
-        // C1 (local rows): w = rho .* (A_g p)
+        // C1 (my rows): w = rho .* (A_g p), pushed to every rank
         for (int base = m0; base < m1; base += 2 * NGM) {
           const int rowA = base + grp_m, rowB = rowA + NGM;
           const bool okA = rowA < m1, okB = rowB < m1;
           double accA, accB;
-          dot_pair<LGM>(a.A, a.p, rowA, okA, a.A, a.p, rowB, okB, lane_m, accA, accB);
+          dot_pair<LGM, 3, 3>(a.A, a.p, rowA, okA, a.A, a.p, rowB, okB, lane_m, accA, accB);
           accA = group_sum<LGM>(accA);
           accB = group_sum<LGM>(accB);
           if (lane_m == 0) {
-            if (okA) a.w[rowA] = a.rho_v[rowA] * accA;
-            if (okB) a.w[rowB] = a.rho_v[rowB] * accB;
+            if (okA) a.w[rowA] = __ldcg(a.rho_v + rowA) * accA;
+            if (okB) a.w[rowB] = __ldcg(a.rho_v + rowB) * accB;
           }
         }
-        B200QP_BARRIER_OR_DIE();
-        mark(1);
-        // C2a: partial A_g' w over all n rows
-        for (int base = f0; base < f1; base += 2 * NGN) {
-          const int rowA = base + grp_n, rowB = rowA + NGN;
-          const bool okA = rowA < f1, okB = rowB < f1;
-          double accA, accB;
-          dot_pair<LGN>(a.At, a.w, rowA, okA, a.At, a.w, rowB, okB, lane_n, accA, accB);
-          accA = group_sum<LGN>(accA);
-          accB = group_sum<LGN>(accB);
-          if (lane_n == 0) {
-            if (okA) my_part_w[rowA] = accA;
-            if (okB) my_part_w[rowB] = accB;
-          }
-        }
+        __syncthreads();
+        push_rows(x.wf, wfull, mlo + m0, mlo + m1);
         B200QP_XBAR_OR_DIE(0, nullptr, 0u);
-        mark(6);
-        // C2b: my slice: Kp = sum_h partial_h + P p + sigma p ; <p, Kp> partial ; push Kp
-        gather_partials(false);
+        mark(1);
+        // C2 (my slice): Kp = P p + sigma p + A' w ; <p, Kp> partial
         double v1[1] = {0.0};
         for (int base = s0; base < s1; base += NGN) {
           const int row = base + grp_n;
           const bool valid = row < s1;
-          const double acc = group_sum<LGN>(row_dot<LGN>(a.P, a.p, row, valid, lane_n));
+          double accP, accA;
+          dot_pair<LGN, 1, 4>(a.P, a.p, row, valid, a.At, wfull, row, valid, lane_n, accP, accA);
+          const double acc = group_sum<LGN>(accP + accA);
           if (valid && lane_n == 0) {
             const double pj = __ldcg(a.p + row);
-            const double kpj = acc + sigma * pj + __ldcg(x.sum_w + row);
+            const double kpj = acc + sigma * pj;
             a.kp[row] = kpj;
             v1[0] += pj * kpj;
           }
         }
-        __syncthreads();
-        push_rows(x.kp, a.kp);
         double* bk = bank();
         block_reduce_store<1>(v1, 0u, bk, G, s_red);
         B200QP_XBAR_OR_DIE(1, bk, 0u);
@@ -524,38 +476,43 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
         if (!(pkp > 0.0)) { status = 9; break; }
         const double aj = rz / pkp;
         cg_total++;
-        // C3 (replicated, uniform partition): d += a p ; r -= a Kp ; <r, Minv r> ; |r|inf
+        // C3 (my slice): d += a p ; r -= a Kp ; <r, Minv r> ; |r|inf
         double v2[2] = {0.0, 0.0};
-        for (int i = u0 + tid; i < u1; i += NT) {
+        for (int i = s0 + tid; i < s1; i += NT) {
           const double pi = __ldcg(a.p + i);
           a.d[i] = (j == 0) ? aj * pi : fma(aj, pi, __ldcg(a.d + i));
-          const double ri = fma(-aj, __ldcg(a.kp + i), __ldcg(a.r + i));
+          const double ri = fma(-aj, a.kp[i], a.r[i]);
           a.r[i] = ri;
-          v2[0] += ri * __ldcg(a.Minv + i) * ri;
+          v2[0] += ri * a.Minv[i] * ri;
           v2[1] = nanmax(v2[1], fabs(ri));
         }
         have_d = true;
         bk = bank();
         block_reduce_store<2>(v2, 2u, bk, G, s_red);
-        B200QP_BARRIER_OR_DIE();
-        grid_reduce_load<2>(bk, G, 2u, s_tot);
+        B200QP_XBAR_OR_DIE(2, bk, 2u);
         mark(3);
         const double rz_new = s_tot[0], rmax = s_tot[1];
         if (!(rmax > tol) || j + 1 == a.cg_max_iter) break;
+        // C4 (my slice): p = Minv r + b p, pushed to every rank
         const double bj = rz_new / rz;
         rz = rz_new;
-        for (int i = u0 + tid; i < u1; i += NT) a.p[i] = fma(bj, __ldcg(a.p + i), __ldcg(a.Minv + i) * __ldcg(a.r + i));
-        B200QP_BARRIER_OR_DIE();
+        for (int i = s0 + tid; i < s1; i += NT) a.p[i] = fma(bj, __ldcg(a.p + i), a.Minv[i] * a.r[i]);
+        __syncthreads();
+        push_rows(x.p, a.p, s0, s1);
+        B200QP_XBAR_OR_DIE(0, nullptr, 0u);
         mark(4);
       }
       if (status) break;
     }
-    if (!have_d) {
+    if (have_d) {
+      push_rows(x.d, a.d, s0, s1);               // the Z phase gathers from the whole step
+    } else {
       for (int i = u0 + tid; i < u1; i += NT) a.d[i] = 0.0;
-      B200QP_BARRIER_OR_DIE();
     }
+    B200QP_XBAR_OR_DIE(0, nullptr, 0u);
+    mark(6);
 
-    // ---------------------------------------------------------------- Z phase (local rows)
+    // ---------------------------------------------------------------- Z phase (my rows)
     const int kn = k + 1;
     const bool last_n = (kn >= a.max_iter);
     const bool full_n = ((a.check_term > 0 && (kn % a.check_term) == 0) || last_n) ||
@@ -567,7 +524,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
       v[Z_VU] = NEG_INF; v[Z_VL] = NEG_INF;
       auto z_row = [&](int row, double ad) {
           const double ax_old = a.ax[row], z_old = a.z[row], y_old = a.y[row];
-          const double rv = a.rho_v[row], ri = a.rho_inv[row], li = a.l[row], ui = a.u[row];
+          const double rv = __ldcg(a.rho_v + row), ri = __ldcg(a.rho_inv + row), li = a.l[row], ui = a.u[row];
           const double zt = ax_old + ad;
           const double zr = alpha * zt + (1.0 - alpha) * z_old;
           const double zn = fmin(fmax(zr + ri * y_old, li), ui);
@@ -577,6 +534,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
           a.z[row] = zn; a.y[row] = yn; a.ax[row] = axn;
           a.w2[row] = rv * (zn - axn) - yn;
           if (full_n) {
+            yfull[mlo + row] = yn;
             const double ei = Einv_t ? Einv_t[row] : 1.0;
             const double pr = axn - zn;
             v[Z_SPRIM] = nanmax(v[Z_SPRIM], fabs(pr));
@@ -603,7 +561,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
         const int rowA = base + grp_m, rowB = rowA + NGM;
         const bool okA = rowA < m1, okB = rowB < m1;
         double adA, adB;
-        dot_pair<LGM>(a.A, a.d, rowA, okA, a.A, a.d, rowB, okB, lane_m, adA, adB);
+        dot_pair<LGM, 3, 3>(a.A, a.d, rowA, okA, a.A, a.d, rowB, okB, lane_m, adA, adB);
         adA = group_sum<LGM>(adA);
         adB = group_sum<LGM>(adB);
         if (lane_m == 0) {
@@ -611,8 +569,12 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
           if (okB) z_row(rowB, adB);
         }
       }
-      for (int i = u0 + tid; i < u1; i += NT) a.x[i] = fma(alpha, __ldcg(a.d + i), __ldcg(a.x + i));
+      for (int i = u0 + tid; i < u1; i += NT) a.x[i] = fma(alpha, __ldcg(a.d + i), __ldcg(a.x + i));   // replicated
+      __syncthreads();
+      push_rows(x.w2f, w2full, mlo + m0, mlo + m1);
       if (full_n) {
+        push_rows(x.yf, yfull, mlo + m0, mlo + m1);
+        push_rows(x.wf, wfull, mlo + m0, mlo + m1);        // projected delta_y, for the primal-infeasibility norm
         double* bk = bank();
         block_reduce_store<Z_K>(v, Z_MAXMASK, bk, G, s_red);
         B200QP_XBAR_OR_DIE(Z_K, bk, Z_MAXMASK);
@@ -621,7 +583,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
         t_prim = s_tot[Z_TPRIM]; t_ax = s_tot[Z_TAX]; t_z = s_tot[Z_TZ];
         ndy = s_tot[Z_NDY]; lhs = s_tot[Z_LHS]; vu = s_tot[Z_VU]; vl = s_tot[Z_VL]; sup = s_tot[Z_SUP];
       } else {
-        B200QP_BARRIER_OR_DIE();
+        B200QP_XBAR_OR_DIE(0, nullptr, 0u);
       }
     }
     mark(5);

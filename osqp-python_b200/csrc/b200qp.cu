@@ -159,10 +159,9 @@ struct Work {
     char* peer[MAXW] = {nullptr};      // base of every rank's region in my address space
     bool opened[MAXW] = {false};       // cudaIpcOpenMemHandle'd (must be closed)
     bool connected = false;
-    DevCsr Atg;                        // A_g' : n x m_g, compact
-    DBuf<double> sum_w, sum_y, xtot;
+    DBuf<double> xtot;
     DBuf<unsigned long long> release;
-    DBuf<int> part_m, part_nfull, part_slice, part_uni;
+    DBuf<int> part_m, part_slice, part_uni, part_mall;
     int G = 1, lgn = 8, lgm = 8;
     unsigned long long xepoch = 0;
     bool broken = false;
@@ -185,8 +184,8 @@ struct Work {
     for (int h = 0; h < MAXW; ++h)
       if (dist.opened[h] && dist.peer[h]) cudaIpcCloseMemHandle(dist.peer[h]);
     if (dist.region) cudaFree(dist.region);
-    dist.Atg.free(); dist.sum_w.free(); dist.sum_y.free(); dist.xtot.free(); dist.release.free();
-    dist.part_m.free(); dist.part_nfull.free(); dist.part_slice.free(); dist.part_uni.free();
+    dist.xtot.free(); dist.release.free();
+    dist.part_m.free(); dist.part_slice.free(); dist.part_uni.free(); dist.part_mall.free();
     if (h_x) cudaFreeHost(h_x);
     if (h_y) cudaFreeHost(h_y);
     if (h_pc) cudaFreeHost(h_pc);
@@ -197,17 +196,18 @@ struct Work {
   }
 };
 
-// shared-region layout of a multi-GPU rank (same offsets on every rank)
+// shared-region layout of a multi-GPU rank (same offsets on every rank): control block, arrival flags, barrier
+// payload, then the five gathered vectors -- w, w2, y (length m) and p, d (length n)
 struct RegionLayout {
-  size_t ctrl, flags, payload, part_w, part_y, r, p, kp, Minv, total;
-  explicit RegionLayout(size_t n) {
+  size_t ctrl, flags, payload, wf, w2f, yf, p, d, total;
+  RegionLayout(size_t n, size_t m) {
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t o = 0;
     ctrl = o; o = al(o + sizeof(Ctrl));
     flags = o; o = al(o + MAXW * sizeof(unsigned long long));
     payload = o; o = al(o + 2 * MAXW * KMAX * sizeof(double));
-    const size_t vec = al(n * sizeof(double));
-    part_w = o; o += vec; part_y = o; o += vec; r = o; o += vec; p = o; o += vec; kp = o; o += vec; Minv = o; o += vec;
+    const size_t vn = al(n * sizeof(double)), vm = al(std::max<size_t>(m, 1) * sizeof(double));
+    wf = o; o += vm; w2f = o; o += vm; yf = o; o += vm; p = o; o += vn; d = o; o += vn;
     total = o;
   }
 };
@@ -338,18 +338,16 @@ KArgs make_args(b200qp_solver* sv) {
   a.rho_is_vec = st->rho_is_vec; a.check_dualgap = st->check_dualgap; a.verbose = st->verbose;
   a.polish_mode = 0;
   if (w->dist.connected) {
-    // row slab views: A_g = rows [mlo, mhi) of CSR(A) (pointer offset), compact A_g', slab of every m-vector;
-    // r, p, Kp, Minv live in the shared region so that the other ranks can push their slices into them
+    // row slab views: A_g = rows [mlo, mhi) of CSR(A) (pointer offset) and the slab of every m-vector; A' and P
+    // stay whole (the kernel walks the rows of its variable slice).  w, w2, p, d already live in the shared region
+    // (borrowed at dist_setup), so the generic pointers above are the full, peer-visible copies.
     Work::Dist& d = w->dist;
     const int mlo = d.mlo, mg = d.mhi - d.mlo;
-    RegionLayout L(w->n);
+    RegionLayout L(w->n, w->m);
     a.m = mg; a.G = d.G;
     a.A = CsrMat{mg, w->n, w->A.nnz, w->A.ptr.p + mlo, w->A.idx.p, w->A.val.p};
-    a.At = d.Atg.view();
     a.l += mlo; a.u += mlo; a.E += mlo; a.Einv += mlo; a.ctype += mlo;
     a.z += mlo; a.y += mlo; a.ax += mlo; a.w2 += mlo; a.w += mlo; a.rho_v += mlo; a.rho_inv += mlo;
-    a.r = (double*)(d.region + L.r); a.p = (double*)(d.region + L.p); a.kp = (double*)(d.region + L.kp);
-    a.Minv = (double*)(d.region + L.Minv);
     a.ctrl = (Ctrl*)(d.region + L.ctrl);
     a.part_m = d.part_m.p;
     a.part_n = d.part_uni.p;
@@ -368,20 +366,21 @@ admm_dist_fn pick_kernel_dist(int lgn, int lgm) {
 XArgs make_xargs(Work* w) {
   XArgs x{};
   Work::Dist& d = w->dist;
-  RegionLayout L(w->n);
+  RegionLayout L(w->n, w->m);
   x.rank = d.rank; x.world = d.world;
+  x.mlo = d.mlo; x.mtot = w->m;
   for (int h = 0; h <= d.world; ++h) x.slice[h] = d.slice[h];
   for (int h = 0; h < d.world; ++h) {
     char* b = d.peer[h];
-    x.part_w[h] = (double*)(b + L.part_w); x.part_y[h] = (double*)(b + L.part_y);
-    x.r[h] = (double*)(b + L.r); x.p[h] = (double*)(b + L.p); x.kp[h] = (double*)(b + L.kp);
-    x.Minv[h] = (double*)(b + L.Minv);
+    x.wf[h] = (double*)(b + L.wf); x.w2f[h] = (double*)(b + L.w2f); x.yf[h] = (double*)(b + L.yf);
+    x.p[h] = (double*)(b + L.p); x.d[h] = (double*)(b + L.d);
     x.flags[h] = (unsigned long long*)(b + L.flags);
     x.payload[h] = (double*)(b + L.payload);
     x.abort_flag[h] = &((Ctrl*)(b + L.ctrl))->abort;
   }
-  x.sum_w = d.sum_w.p; x.sum_y = d.sum_y.p; x.xtot = d.xtot.p; x.release = d.release.p;
-  x.part_nfull = d.part_nfull.p; x.part_slice = d.part_slice.p; x.part_uni = d.part_uni.p;
+  x.xtot = d.xtot.p; x.release = d.release.p;
+  x.part_slice = d.part_slice.p; x.part_uni = d.part_uni.p; x.part_mall = d.part_mall.p;
+  x.ctype_full = w->ctype.p; x.rho_full = w->rho_v.p; x.rho_inv_full = w->rho_inv.p;
   x.xepoch0 = d.xepoch;
   return x;
 }
@@ -1163,7 +1162,7 @@ extern "C" {
 // fused into the persistent kernel (admm_kernel_dist.cuh).
 
 static int dist_grid(Work* w, int share) {
-  const long long work = (long long)w->P.nnz + 2LL * w->A.nnz / std::max(1, w->dist.world) + 4LL * (w->n + w->m);
+  const long long work = ((long long)w->P.nnz + 2LL * w->A.nnz + 4LL * (w->n + w->m)) / std::max(1, w->dist.world) + 2LL * w->n;
   long long want = work / 8192;
   if (const char* e = std::getenv("B200QP_GRID")) want = std::atoll(e);
   const int cap = std::max(1, w->max_coop_dist / std::max(1, share));
@@ -1185,43 +1184,29 @@ b200qp_int b200qp_dist_setup(b200qp_solver** solverp, b200qp_int rank, b200qp_in
     CK(cudaSetDevice(w->device));
     cudaStream_t s = w->stream;
     d.rank = rank; d.world = world;
-    // row slabs balanced by nnz(A); variable slices balanced by nnz(P) -- same on every rank
+    // launch geometry first: the partitions below use the lane counts (identical on all ranks)
+    d.lgn = w->lgn;
+    d.lgm = w->lgm;
+    // row slabs balanced by the cost of the A rows; variable slices by the cost of the P + A' rows -- same on every rank
     std::vector<int> rows, sl;
-    make_partition(m, world, {&w->A.h_ptr}, rows);
-    make_partition(n, world, {&w->P.h_ptr}, sl);
+    make_partition(m, world, {&w->A.h_ptr}, rows, d.lgm);
+    make_partition(n, world, {&w->P.h_ptr, &w->At.h_ptr}, sl, d.lgn);
     d.mlo = rows[rank]; d.mhi = rows[rank + 1];
     for (int h = 0; h <= world; ++h) d.slice[h] = sl[h];
     const int mlo = d.mlo, mhi = d.mhi, mg = mhi - mlo;
-    // compact A_g' from the (scaled) CSR(A') = CSC(A) arrays: keep row indices in [mlo, mhi)
-    const int nnzA = w->A.nnz;
-    std::vector<double> atx(nnzA);
-    if (nnzA) CK(cudaMemcpyAsync(atx.data(), w->At.val.p, (size_t)nnzA * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    std::vector<int> gp(n + 1, 0), gi;
-    std::vector<double> gx;
-    for (int j = 0; j < n; ++j) {
-      for (int k = A->p[j]; k < A->p[j + 1]; ++k) {
-        const int i = A->i[k];
-        if (i >= mlo && i < mhi) { gi.push_back(i - mlo); gx.push_back(atx[k]); }
-      }
-      gp[j + 1] = (int)gi.size();
-    }
-    d.Atg.upload(n, std::max(mg, 1), gp, gi, gx, s);
-    // shared region
-    RegionLayout L(n);
+    // shared region; the gathered vectors w, w2, p, d of the workspace move into it (peers push into them)
+    RegionLayout L(n, m);
     d.region_bytes = L.total;
     CK(cudaMalloc(&d.region, L.total));
     CK(cudaMemsetAsync(d.region, 0, L.total, s));
-    CK(cudaMemcpyAsync(d.region + L.Minv, w->Minv.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     CK(cudaStreamSynchronize(s));
-    w->Minv.borrow((double*)(d.region + L.Minv), n);     // later Jacobi refreshes land in the shared copy
+    w->w.borrow((double*)(d.region + L.wf), m);
+    w->w2.borrow((double*)(d.region + L.w2f), m);
+    w->p.borrow((double*)(d.region + L.p), n);
+    w->d.borrow((double*)(d.region + L.d), n);
     d.peer[rank] = d.region;
-    d.sum_w.alloc(n); d.sum_y.alloc(n); d.xtot.alloc(2 * KMAX); d.release.alloc(1);
-    d.sum_w.zero(s); d.sum_y.zero(s); d.xtot.zero(s); d.release.zero(s);
-    // launch geometry (identical on all ranks: the replicated reductions must agree bit for bit)
-    d.lgn = pick_lg(n ? (double)(w->P.nnz / world + d.Atg.nnz) / n : 1.0);
-    d.lgn = pick_lg(n ? (double)(w->P.nnz + w->A.nnz) / n / 2 : 1.0);
-    d.lgm = w->lgm;
+    d.xtot.alloc(2 * KMAX); d.release.alloc(1);
+    d.xtot.zero(s); d.release.zero(s);
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)pick_kernel_dist(d.lgn, d.lgm), NT, 0));
     cudaDeviceProp prop;
@@ -1229,25 +1214,24 @@ b200qp_int b200qp_dist_setup(b200qp_solver** solverp, b200qp_int rank, b200qp_in
     if (occ < 1) throw (int)B200QP_ALGEBRA_LOAD_ERROR;
     w->max_coop_dist = occ * prop.multiProcessorCount;
     d.G = dist_grid(w, std::max(1, (int)ranks_on_device));
-    std::vector<int> pm, pf, ps, pu(d.G + 1);
+    std::vector<int> pm, ps, pu(d.G + 1), pa(d.G + 1);
     {   // local rows of A_g: weights from the global row pointer, shifted
       std::vector<int> lp(mg + 1);
       for (int i = 0; i <= mg; ++i) lp[i] = w->A.h_ptr[mlo + i] - w->A.h_ptr[mlo];
       make_partition(mg, d.G, {&lp}, pm, d.lgm);
     }
-    make_partition(n, d.G, {&d.Atg.h_ptr}, pf, d.lgn);
-    {   // my slice by nnz(P): partition the sub-range, then shift to absolute row numbers
+    {   // my slice by the cost of its P and A' rows: partition the sub-range, then shift to absolute row numbers
       const int a0 = d.slice[rank], a1 = d.slice[rank + 1];
-      std::vector<int> lp(a1 - a0 + 1);
-      for (int i = 0; i <= a1 - a0; ++i) lp[i] = w->P.h_ptr[a0 + i] - w->P.h_ptr[a0];
-      make_partition(a1 - a0, d.G, {&lp}, ps, d.lgn);
+      std::vector<int> lp(a1 - a0 + 1), lt(a1 - a0 + 1);
+      for (int i = 0; i <= a1 - a0; ++i) { lp[i] = w->P.h_ptr[a0 + i] - w->P.h_ptr[a0]; lt[i] = w->At.h_ptr[a0 + i] - w->At.h_ptr[a0]; }
+      make_partition(a1 - a0, d.G, {&lp, &lt}, ps, d.lgn);
       for (int& v : ps) v += a0;
     }
-    for (int g = 0; g <= d.G; ++g) pu[g] = (int)((long long)n * g / d.G);
+    for (int g = 0; g <= d.G; ++g) { pu[g] = (int)((long long)n * g / d.G); pa[g] = (int)((long long)m * g / d.G); }
     d.part_m.alloc(d.G + 1); d.part_m.upload(pm.data(), d.G + 1, s);
-    d.part_nfull.alloc(d.G + 1); d.part_nfull.upload(pf.data(), d.G + 1, s);
     d.part_slice.alloc(d.G + 1); d.part_slice.upload(ps.data(), d.G + 1, s);
     d.part_uni.alloc(d.G + 1); d.part_uni.upload(pu.data(), d.G + 1, s);
+    d.part_mall.alloc(d.G + 1); d.part_mall.upload(pa.data(), d.G + 1, s);
     w->red.alloc((size_t)2 * KMAX * std::max(d.G, w->G)); w->red.zero(s);
     CK(cudaStreamSynchronize(s));
     if (world == 1) d.connected = true;
