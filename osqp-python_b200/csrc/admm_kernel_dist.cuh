@@ -231,6 +231,14 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
     }
   };
 
+  // one value of a gathered vector, pushed by the thread that produced it: the NVLink stores then overlap the rest
+  // of the phase instead of queueing up in front of the barrier's system-scope fence
+  auto push_one = [&](double* const* table, int i, double v) {
+#pragma unroll
+    for (int h = 0; h < MAXW; ++h)
+      if (h < world && h != rank) st_sys_f64(table[h] + i, v);
+  };
+
   // ------------------------------------------------------------------ init: ax = A_g x, w2 (slab) -> everybody
   for (int base = m0; base < m1; base += NGM) {
     const int row = base + grp_m;
@@ -287,6 +295,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
         const double pj = a.Minv[row] * rj;
         a.r[row] = rj;
         a.p[row] = pj;
+        push_one(x.p, row, pj);
         v[R_RZ] += rj * pj;
         v[R_R0] = nanmax(v[R_R0], fabs(rj));
         if (full) {
@@ -309,8 +318,6 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
     }
     if (full && tid == 0)
       v[R_TL] = ((double)(global_timer_ns() - t_start) > a.time_limit_ns) ? 1.0 : 0.0;
-    __syncthreads();
-    push_rows(x.p, a.p, s0, s1);
     double* bk = bank();
     block_reduce_store<R_K>(v, R_MAXMASK, bk, G, s_red);
     if (!xs.template barrier_x<R_K>(bk, R_MAXMASK, s_tot)) return false;
@@ -445,12 +452,10 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
           accA = group_sum<LGM>(accA);
           accB = group_sum<LGM>(accB);
           if (lane_m == 0) {
-            if (okA) a.w[rowA] = __ldcg(a.rho_v + rowA) * accA;
-            if (okB) a.w[rowB] = __ldcg(a.rho_v + rowB) * accB;
+            if (okA) { const double v = __ldcg(a.rho_v + rowA) * accA; a.w[rowA] = v; push_one(x.wf, mlo + rowA, v); }
+            if (okB) { const double v = __ldcg(a.rho_v + rowB) * accB; a.w[rowB] = v; push_one(x.wf, mlo + rowB, v); }
           }
         }
-        __syncthreads();
-        push_rows(x.wf, wfull, mlo + m0, mlo + m1);
         B200QP_XBAR_OR_DIE(0, nullptr, 0u);
         mark(1);
         // C2 (my slice): Kp = P p + sigma p + A' w ; <p, Kp> partial
@@ -496,9 +501,11 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
         // C4 (my slice): p = Minv r + b p, pushed to every rank
         const double bj = rz_new / rz;
         rz = rz_new;
-        for (int i = s0 + tid; i < s1; i += NT) a.p[i] = fma(bj, __ldcg(a.p + i), a.Minv[i] * a.r[i]);
-        __syncthreads();
-        push_rows(x.p, a.p, s0, s1);
+        for (int i = s0 + tid; i < s1; i += NT) {
+          const double v = fma(bj, __ldcg(a.p + i), a.Minv[i] * a.r[i]);
+          a.p[i] = v;
+          push_one(x.p, i, v);
+        }
         B200QP_XBAR_OR_DIE(0, nullptr, 0u);
         mark(4);
       }
@@ -532,9 +539,12 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
           const double yn = y_old + dy;
           const double axn = fma(alpha, ad, ax_old);
           a.z[row] = zn; a.y[row] = yn; a.ax[row] = axn;
-          a.w2[row] = rv * (zn - axn) - yn;
+          const double w2n = rv * (zn - axn) - yn;
+          a.w2[row] = w2n;
+          push_one(x.w2f, mlo + row, w2n);
           if (full_n) {
             yfull[mlo + row] = yn;
+            push_one(x.yf, mlo + row, yn);
             const double ei = Einv_t ? Einv_t[row] : 1.0;
             const double pr = axn - zn;
             v[Z_SPRIM] = nanmax(v[Z_SPRIM], fabs(pr));
@@ -549,6 +559,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
             else if (!ufin) dyp = fmin(dy, 0.0);
             else if (!lfin) dyp = fmax(dy, 0.0);
             a.w[row] = dyp;
+            push_one(x.wf, mlo + row, dyp);                  // projected delta_y, for the primal-infeasibility norm
             v[Z_NDY] = nanmax(v[Z_NDY], fabs((E_t ? E_t[row] : 1.0) * dyp));
             v[Z_LHS] += (ufin ? ui * fmax(dyp, 0.0) : 0.0) + (lfin ? li * fmin(dyp, 0.0) : 0.0);
             const double adx = ei * alpha * ad;
@@ -570,11 +581,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
         }
       }
       for (int i = u0 + tid; i < u1; i += NT) a.x[i] = fma(alpha, __ldcg(a.d + i), __ldcg(a.x + i));   // replicated
-      __syncthreads();
-      push_rows(x.w2f, w2full, mlo + m0, mlo + m1);
       if (full_n) {
-        push_rows(x.yf, yfull, mlo + m0, mlo + m1);
-        push_rows(x.wf, wfull, mlo + m0, mlo + m1);        // projected delta_y, for the primal-infeasibility norm
         double* bk = bank();
         block_reduce_store<Z_K>(v, Z_MAXMASK, bk, G, s_red);
         B200QP_XBAR_OR_DIE(Z_K, bk, Z_MAXMASK);
