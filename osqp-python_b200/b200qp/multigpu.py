@@ -186,7 +186,7 @@ def bench(args, rank, world, local, B):
                        "pcg_iters_per_admm_iter": cg / max(iters, 1), "status": res.info.status,
                        "partition": f"{world} row slabs of A + {world} variable slices of P and A'; p, d, w, w2 all-gathered by "
                                     "NVLink stores fused into the producing phases of the persistent kernel, x replicated",
-                       "phase_ms_per_step_rank0": dict(zip(["R_slice_push_p", "C1_Ap_push_w", "C2_Kp_slice", "C3_slice_dots", "C4_push_p", "Z_push_w2",
+                       "phase_ms_per_step_rank0": dict(zip(["R_slice_push_u", "B_Au_push_t", "C_Ku_slice", "V_slice_push_u", "x4", "Z_push_w2",
                                                             "gather_d", "x7"], [round(v / args.steps, 3) for v in phases])),
                        "l2": "inputs larger than L2; no flush between steps", "grid": f"{st['grid']}x{st['block']} per GPU",
                        "setup_s": t_setup, "settings": dict(B.SOLVE_KW)},

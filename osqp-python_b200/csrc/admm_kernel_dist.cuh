@@ -12,8 +12,11 @@
 // flags in peer-mapped memory; the barrier carries the scalar partials (dots, norms) as payload, folded in rank
 // order, so all ranks see identical bits and take identical control decisions.
 //
-// Per PCG iteration: C1 (A_g p -> push w) | C2 (slice rows: P p + sigma p + A' w, <p,Kp>) | C3 (slice: d, r, dots)
-// | C4 (slice: p -> push p): four cross-GPU barriers, 2 x 8 (G-1)/G MB pushed per rank, no replicated work.
+// The PCG is the single-reduction variant of Chronopoulos & Gear (same iterates as the textbook recurrence in exact
+// arithmetic: <p,Kp> = <w,u> - beta <r,u> / alpha_prev with u = M^-1 r, w = K u), because every global reduction is a
+// cross-GPU barrier here.  Per PCG iteration: B (t = rho A_g u -> push t) | C (slice rows: w = P u + sigma u + A' t,
+// <w,u>) | V (slice: p, s, d, r, u = M^-1 r -> push u, <r,u>, |r|inf): three cross-GPU barriers, 2 x 8 (G-1)/G MB
+// pushed per rank, no replicated work.
 // (The first version reduce-scattered partial A_g' w products of full length n: every rank walked all n rows of a
 // matrix with 10/G entries per row and repeated the C3 / C4 passes -- it stopped scaling at 2 GPUs, profiles/r1d.)
 #pragma once
@@ -40,6 +43,7 @@ struct XArgs {
   double* xtot;                     // [2][KMAX] totals published by CTA 0 to the other CTAs
   unsigned long long* release;      // local release counter of the cross-GPU barrier
   const int *part_slice, *part_uni, *part_mall;   // CTA partitions: my slice (cost of P + A' rows), uniform [0,n), uniform [0,mtot)
+  double *ps, *ss;                  // slice-local search direction p and s = K p of the single-reduction PCG
   const int* ctype_full;            // full-length typing / rho vectors: every rank re-derives all of rho at a rho update
   double *rho_full, *rho_inv_full;
   unsigned long long xepoch0;       // cross-GPU barriers completed by earlier launches (flags are never reset)
@@ -72,10 +76,12 @@ struct DistSync {
   const XArgs* x;
   unsigned long long xepoch;     // cross-GPU barriers passed
 
+  // pushed = this CTA issued peer stores since the last barrier (they must be visible system-wide before the
+  // arrival flag); phases that only produce local data and a payload get away with a device-scope fence
   template <int K>
-  __device__ __forceinline__ bool barrier_x(const double* bank, unsigned maxmask, double* s_tot) {
+  __device__ __forceinline__ bool barrier_x(const double* bank, unsigned maxmask, double* s_tot, bool pushed = true) {
     const int G = g->G, world = x->world, tid = threadIdx.x;
-    __threadfence_system();
+    if (pushed) __threadfence_system(); else __threadfence();
     __syncthreads();
     g->epoch++;
     xepoch++;
@@ -171,7 +177,7 @@ struct DistSync {
   }
 };
 
-#define B200QP_XBAR_OR_DIE(K, bank, mask) do { if (!xs.template barrier_x<K>(bank, mask, s_tot)) { if (blockIdx.x == 0 && threadIdx.x == 0) a.out->aborted = 1; return; } } while (0)
+#define B200QP_XBAR_OR_DIE(K, bank, mask) do { if (!xs.template barrier_x<K>(bank, mask, s_tot, true)) { if (blockIdx.x == 0 && threadIdx.x == 0) a.out->aborted = 1; return; } } while (0)
 
 template <int LGN, int LGM>
 __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant__ KArgs a, const __grid_constant__ XArgs x) {
@@ -351,7 +357,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
     }
     double* bk = bank();
     block_reduce_store<1>(v, 1u, bk, G, s_red);
-    ok = xs.template barrier_x<1>(bk, 1u, s_tot);
+    ok = xs.template barrier_x<1>(bk, 1u, s_tot, false);
     return ok ? s_tot[0] : 0.0;
   };
 
@@ -383,6 +389,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
     return 0;
   };
 
+#define B200QP_XBAR_LOCAL_OR_DIE(K, bank, mask) do { if (!xs.template barrier_x<K>(bank, mask, s_tot, false)) { if (blockIdx.x == 0 && threadIdx.x == 0) a.out->aborted = 1; return; } } while (0)
 #define B200QP_DIE() do { if (cta == 0 && tid == 0) a.out->aborted = 1; return; } while (0)
 
   // ================================================================== main loop
@@ -438,12 +445,14 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
       }
     }
 
-    // ---------------------------------------------------------------- PCG on K d = r
+    // ---------------------------------------------------------------- PCG on K d = r (single-reduction recurrence)
+    // a.p (full, gathered) holds u = M^-1 r: the R phase left u_0 there and <r_0, u_0> in rz
     bool have_d = false;
     if (r0max > 1e-150) {
       const double tol = a.cg_tol_frac * r0max;
+      double gam = rz, gam_prev = rz, alpha_cg = 0.0;
       for (int j = 0; j < a.cg_max_iter; ++j) {
-        // C1 (my rows): w = rho .* (A_g p), pushed to every rank
+        // B (my rows): t = rho .* (A_g u), pushed to every rank
         for (int base = m0; base < m1; base += 2 * NGM) {
           const int rowA = base + grp_m, rowB = rowA + NGM;
           const bool okA = rowA < m1, okB = rowB < m1;
@@ -458,7 +467,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
         }
         B200QP_XBAR_OR_DIE(0, nullptr, 0u);
         mark(1);
-        // C2 (my slice): Kp = P p + sigma p + A' w ; <p, Kp> partial
+        // C (my slice): w = K u = P u + sigma u + A' t ; <w, u> partial
         double v1[1] = {0.0};
         for (int base = s0; base < s1; base += NGN) {
           const int row = base + grp_n;
@@ -467,28 +476,36 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
           dot_pair<LGN, 1, 4>(a.P, a.p, row, valid, a.At, wfull, row, valid, lane_n, accP, accA);
           const double acc = group_sum<LGN>(accP + accA);
           if (valid && lane_n == 0) {
-            const double pj = __ldcg(a.p + row);
-            const double kpj = acc + sigma * pj;
-            a.kp[row] = kpj;
-            v1[0] += pj * kpj;
+            const double uj = __ldcg(a.p + row);
+            const double wj = acc + sigma * uj;
+            a.kp[row] = wj;
+            v1[0] += uj * wj;
           }
         }
         double* bk = bank();
         block_reduce_store<1>(v1, 0u, bk, G, s_red);
-        B200QP_XBAR_OR_DIE(1, bk, 0u);
+        B200QP_XBAR_LOCAL_OR_DIE(1, bk, 0u);
         mark(2);
-        const double pkp = s_tot[0];
+        const double delta = s_tot[0];
+        const double bj = (j == 0) ? 0.0 : gam / gam_prev;
+        const double pkp = (j == 0) ? delta : delta - bj * gam / alpha_cg;      // = <p, K p>
         if (!(pkp > 0.0)) { status = 9; break; }
-        const double aj = rz / pkp;
+        alpha_cg = gam / pkp;
         cg_total++;
-        // C3 (my slice): d += a p ; r -= a Kp ; <r, Minv r> ; |r|inf
+        // V (my slice): p = u + b p ; s = w + b s ; d += a p ; r -= a s ; u = Minv r (pushed) ; <r, u> ; |r|inf
         double v2[2] = {0.0, 0.0};
         for (int i = s0 + tid; i < s1; i += NT) {
-          const double pi = __ldcg(a.p + i);
-          a.d[i] = (j == 0) ? aj * pi : fma(aj, pi, __ldcg(a.d + i));
-          const double ri = fma(-aj, a.kp[i], a.r[i]);
+          const double ui = __ldcg(a.p + i), wi = a.kp[i];
+          const double pi = (j == 0) ? ui : fma(bj, x.ps[i], ui);
+          const double si = (j == 0) ? wi : fma(bj, x.ss[i], wi);
+          x.ps[i] = pi; x.ss[i] = si;
+          a.d[i] = (j == 0) ? alpha_cg * pi : fma(alpha_cg, pi, __ldcg(a.d + i));
+          const double ri = fma(-alpha_cg, si, a.r[i]);
           a.r[i] = ri;
-          v2[0] += ri * a.Minv[i] * ri;
+          const double un = a.Minv[i] * ri;
+          a.p[i] = un;
+          push_one(x.p, i, un);
+          v2[0] += ri * un;
           v2[1] = nanmax(v2[1], fabs(ri));
         }
         have_d = true;
@@ -496,18 +513,10 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
         block_reduce_store<2>(v2, 2u, bk, G, s_red);
         B200QP_XBAR_OR_DIE(2, bk, 2u);
         mark(3);
-        const double rz_new = s_tot[0], rmax = s_tot[1];
+        gam_prev = gam;
+        gam = s_tot[0];
+        const double rmax = s_tot[1];
         if (!(rmax > tol) || j + 1 == a.cg_max_iter) break;
-        // C4 (my slice): p = Minv r + b p, pushed to every rank
-        const double bj = rz_new / rz;
-        rz = rz_new;
-        for (int i = s0 + tid; i < s1; i += NT) {
-          const double v = fma(bj, __ldcg(a.p + i), a.Minv[i] * a.r[i]);
-          a.p[i] = v;
-          push_one(x.p, i, v);
-        }
-        B200QP_XBAR_OR_DIE(0, nullptr, 0u);
-        mark(4);
       }
       if (status) break;
     }

@@ -380,6 +380,7 @@ XArgs make_xargs(Work* w) {
   }
   x.xtot = d.xtot.p; x.release = d.release.p;
   x.part_slice = d.part_slice.p; x.part_uni = d.part_uni.p; x.part_mall = d.part_mall.p;
+  x.ps = w->tmp_n.p; x.ss = w->tmp_n2.p;
   x.ctype_full = w->ctype.p; x.rho_full = w->rho_v.p; x.rho_inv_full = w->rho_inv.p;
   x.xepoch0 = d.xepoch;
   return x;
