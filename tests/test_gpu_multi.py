@@ -1,8 +1,7 @@
-"""GPU tests of the row-partitioned multi-GPU path (csrc/admm_kernel_dist.cuh).
+"""GPU tests of the multi-GPU path (csrc/admm_kernel_dist.cuh: row slabs + variable slices, all-gather by stores).
 
 On a one-GPU box the ranks share device 0 (each rank is its own cooperative kernel on its own stream;
-the cross-rank protocol -- flags, payloads, fused reduce-scatter/all-gather through peer pointers -- is
-exactly the multi-device one).  With >= 2 visible GPUs the same tests also run one rank per device."""
+the cross-rank protocol -- flags, payloads, pushes through peer pointers -- is exactly the multi-device one).  With >= 2 visible GPUs the same tests also run one rank per device."""
 import numpy as np
 import pytest
 
@@ -69,6 +68,29 @@ def test_group_midsize_random_qp(world):
         assert _rel(r.x, single.x) <= 1e-4 and _rel(r.y, single.y) <= 1e-3
         rep = problems.kkt_report(P, q, A, l, u, r.x, r.y)
         assert rep["prim"] < 1e-4 and rep["dual"] < 1e-4
+
+
+def test_group_world8_virtual_ranks():
+    """The maximum world size (MAXW = 8) on one device: 8 slabs, 8 slices, 7 peers per push."""
+    import osqp
+    from b200qp import problems
+    from b200qp.multigpu import LocalGroup
+    P, q, A, l, u = problems.random_qp(3000, 4000, nnz_per_row=6, seed=5, eq_frac=0.1, onesided_frac=0.1)
+    kw = dict(verbose=False, eps_abs=1e-7, eps_rel=1e-7, max_iter=20000)
+    prob = osqp.OSQP()
+    prob.setup(P, q, A, l, u, **kw)
+    single = prob.solve()
+    assert single.info.status == "solved"
+    grp = LocalGroup(P, q, A, l, u, [0] * 8, **kw)
+    results = grp.solve()
+    r0 = results[0]
+    for r in results:
+        assert r.info.status == "solved" and r.info.iter == r0.info.iter
+        np.testing.assert_array_equal(r.x, r0.x)
+    assert abs(r0.info.iter - single.info.iter) <= max(25, 0.1 * single.info.iter)
+    assert _rel(r0.x, single.x) <= 1e-5 and _rel(r0.y, single.y) <= 1e-4
+    rep = problems.kkt_report(P, q, A, l, u, r0.x, r0.y)
+    assert rep["prim"] < 1e-5 and rep["dual"] < 1e-5
 
 
 def test_group_infeasible_and_unconstrained():
