@@ -105,6 +105,32 @@ def test_no_cpu_fallback_without_device():
         lowlevel.spmv_host(sparse.eye(4, format="csr"), np.ones(4))
 
 
+def test_batch_front_end_without_device_and_shape_checks():
+    """osqp.OSQPBatch: argument shapes are checked on the host; without a CUDA device setup raises (no fallback)."""
+    import osqp
+    import osqp_cuda
+    P = sparse.diags([1.0, 2.0, 3.0], format="csc")
+    A = sparse.eye(3, format="csc")
+    q = np.zeros((4, 3))
+    l, u = -np.ones((4, 3)), np.ones((4, 3))
+    prob = osqp.OSQPBatch()
+    with pytest.raises(AssertionError):
+        prob.setup(P, np.zeros((4, 2)), A, l, u, verbose=False)               # q has the wrong width
+    with pytest.raises(AssertionError):
+        prob.setup(P, q, A, l[:3], u, verbose=False)                          # l has the wrong batch size
+    for name in ("OSQPBatchSolver",):
+        assert hasattr(osqp_cuda, name)
+    for m in ("solve", "update_data_vec", "update_data_mat", "warm_start", "update_settings", "update_rho",
+              "get_solution", "get_info", "get_stats"):
+        assert hasattr(osqp_cuda.OSQPBatchSolver, m)
+    for m in ("adjoint_derivative_compute", "adjoint_derivative_get_mat", "adjoint_derivative_get_vec"):
+        assert hasattr(osqp_cuda.OSQPSolver, m) and hasattr(osqp.OSQP, m)
+    if osqp_cuda.device_count() == 0:
+        with pytest.raises(osqp.OSQPException) as ei:
+            prob.setup(P, q, A, l, u, verbose=False)
+        assert ei.value == osqp.SolverError.OSQP_ALGEBRA_LOAD_ERROR
+
+
 def test_setup_validation_error_codes():
     """Data / settings validation happens before any device work, so it is testable on CPU."""
     import osqp
