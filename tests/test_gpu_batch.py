@@ -353,3 +353,24 @@ def test_non_convex_element_is_reported(mode):
     assert all(int(s) in (7, 9) for s in res.info.status_val), res.info.status
     if np.all(res.info.status_val == 9):
         assert np.all(np.isnan(res.x)) and np.all(np.isnan(res.info.obj_val))
+
+
+def test_batch_with_long_rows_uses_the_16_lane_kernels(mode):
+    """Rows with > 12 entries on average select 16 lanes per row (both matrices): same answers as the oracle."""
+    import osqp
+    from b200qp import problems
+    B, n, m = 4, 50, 60
+    P, q0, A, l, u = problems.random_qp(n, m, nnz_per_row=30, seed=41, eq_frac=0.1, p_pairs=8)
+    assert A.nnz / m > 12 and (sparse.csc_matrix(P).nnz + A.nnz) / n / 2 > 12
+    rng = np.random.default_rng(9)
+    q = q0 + 0.1 * rng.standard_normal((B, n))
+    q[0] = q0
+    kw = dict(eps_abs=1e-9, eps_rel=1e-9, max_iter=50000)
+    prob = osqp.OSQPBatch()
+    prob.setup(P, q, A, l, u, verbose=False, cg_tol_fraction=1e-3, **kw)
+    res = prob.solve()
+    for b in range(B):
+        ora = _oracle_element(P, q[0], A, l, u, q[b], l, u, **kw)
+        assert res.info.status[b] == "solved" and ora.info.status == "solved"
+        assert _rel(res.x[b], ora.x) < REL and _rel(res.y[b], ora.y) < 10 * REL
+        assert abs(res.info.obj_val[b] - ora.info.obj_val) <= REL * max(1.0, abs(ora.info.obj_val))
