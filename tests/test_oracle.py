@@ -148,3 +148,20 @@ def test_oracle_adjoint_derivative_matches_finite_differences():
     Ad = A.toarray()
     fd = approx_fprime(Ad.ravel(), lambda v: loss(P, q, sparse.csc_matrix(v.reshape(m, n)), l, u)[0], 1e-6).reshape(m, n)
     np.testing.assert_allclose(dA, fd, atol=1e-3)
+
+
+def test_batch_element_semantics_setup_then_update_equals_fresh_setup_when_q_is_shared():
+    """The batched engine defines element b as setup(element 0) + update(l[b], u[b]) + solve().  For config 5 (MPC:
+    shared P, q, A; per-element bounds) that is the same solve as a fresh setup on element b, because the
+    equilibration depends on P, A and q only (ref:389-497) -- iteration for iteration."""
+    from b200qp import problems            # tests/conftest.py puts osqp-python_b200/ on sys.path
+    from oracle.osqp_oracle import OracleSolver
+    P, q, A, l, u = problems.mpc_batch(4)
+    for b in (1, 3):
+        s = OracleSolver(P, q, A, l[0], u[0], linsys="direct")
+        s.update(l=l[b], u=u[b])
+        r1 = s.solve()
+        r2 = OracleSolver(P, q, A, l[b], u[b], linsys="direct").solve()
+        assert r1.info.status == r2.info.status == "solved" and r1.info.iter == r2.info.iter
+        np.testing.assert_allclose(r1.x, r2.x, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(r1.y, r2.y, rtol=0, atol=1e-12)
