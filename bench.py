@@ -303,17 +303,26 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    # the secondary lines must never cost the headline line: a failure is recorded, not raised
+    def guarded(key, fn):
+        try:
+            line[key] = fn()
+        except Exception as exc:      # noqa: BLE001
+            line[key] = {"error": f"{type(exc).__name__}: {exc}"}
+        return "error" not in line[key]
+
     if not args.no_spmv:
-        line["spmv"] = spmv_line(A, peak)
+        guarded("spmv", lambda: spmv_line(A, peak))
     if not args.no_structured:
-        line["structured"] = structured_line(args, peak)
-        line["gpu_launches"] += 5
+        if guarded("structured", lambda: structured_line(args, peak)):
+            line["gpu_launches"] += 5
     if not args.no_batch:
         from b200qp import batchbench
-        line["batch"] = batchbench.batch_line(args, with_cpu=not args.no_cpu_baseline)
-        line["gpu_launches"] += args.steps * line["batch"]["gpu_launches_per_step"]
+        if guarded("batch", lambda: batchbench.batch_line(args, with_cpu=not args.no_cpu_baseline)):
+            line["gpu_launches"] += args.steps * line["batch"]["gpu_launches_per_step"]
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_sample(P, q, A, l, u)
+        if not guarded("cpu_baseline", lambda: cpu_baseline_sample(P, q, A, l, u)):
+            line["cpu_baseline"].update({"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed"})
     else:
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "skipped (--no-cpu-baseline)"}
     print(json.dumps(line), flush=True)
