@@ -49,11 +49,6 @@ struct XArgs {
   unsigned long long xepoch0;       // cross-GPU barriers completed by earlier launches (flags are never reset)
 };
 
-__device__ __forceinline__ double ld_peer(const double* p) {   // bypass L1: peer data is not L2-cached locally
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
