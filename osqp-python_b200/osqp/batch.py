@@ -109,3 +109,10 @@ class OSQPBatch(OSQP):
 
     def stats(self):
         return self._solver.get_stats()
+
+    # one adjoint solve per element is a per-solver operation: use osqp.OSQP for derivatives
+    def adjoint_derivative_compute(self, *a, **k):
+        raise NotImplementedError("adjoint derivatives are per solver: use osqp.OSQP (one object per QP)")
+
+    adjoint_derivative_get_mat = adjoint_derivative_compute
+    adjoint_derivative_get_vec = adjoint_derivative_compute
