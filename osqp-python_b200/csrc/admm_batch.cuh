@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
   constexpr int NWB = NTB / 32;
   extern __shared__ double sm[];
   __shared__ int s_qp;
+  __shared__ int s_tl;
   const int n = a.n, m = a.m, tid = threadIdx.x;
   double* const q = sm;
   double* const x = q + n;
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
     double t_prim = 0, t_ax = 0, t_z = 0;
     double ndx = 0, qdx = 0;
     double rz = 0, r0max = 0;
-    bool time_up = false, chk_next = false, adp_next = false;
+    bool time_up = false, tl_stop = false, chk_next = false, adp_next = false;
     int cnt_chk = 0, cnt_adp = 0;
 
     // ---- dense mode: K = P + sigma I + A' rho A formed row by row (thread j owns row j: no atomics), inverted
@@ -461,15 +462,19 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
           }
         }
       }
+      // the clock is sampled every iteration (upstream osqp_solve does; check_termination = 0 must still stop)
       if (DENSE && !full) {          // the mat-vec needs neither <r, p> nor |r|inf: no reduction on plain iterations
+        if (tid == 0) s_tl = ((double)(global_timer_ns() - t_start) > a.time_limit_ns) ? 1 : 0;
         __syncthreads();
+        time_up = s_tl != 0;
         r0max = 1.0;
         return;
       }
-      if (full && tid == 0) v[BR_TL] = ((double)(global_timer_ns() - t_start) > a.time_limit_ns) ? 1.0 : 0.0;
+      if (tid == 0) v[BR_TL] = ((double)(global_timer_ns() - t_start) > a.time_limit_ns) ? 1.0 : 0.0;
       cta_reduce<BR_K, NWB>(v, BR_MAXMASK, s_red, s_tot);
       rz = s_tot[BR_RZ];
       r0max = s_tot[BR_R0];
+      time_up = s_tot[BR_TL] > 0.5;
       if (full) {
         s_dual = s_tot[BR_SDUAL];
         s_ndual = fmax(fmax(s_tot[BR_SATY], s_tot[BR_SPX]), nq_s);
@@ -480,7 +485,6 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
         gap = obj - dobj;
         ndx = s_tot[BR_NDX];
         qdx = s_tot[BR_QDX];
-        time_up = s_tot[BR_TL] > 0.5;
         prim_res = t_prim;
         nprim = fmax(t_ax, t_z);
       }
@@ -539,7 +543,7 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
           if (!status) status = 7;
           break;
         }
-        if (time_up) { status = 8; break; }
+        if (tl_stop) { status = 8; break; }   // the clock ran out during the previous iteration
       }
       if (adp) {   // reference: _osqp.py:880-930 (scaled quantities)
         const double pr = s_prim / (s_nprim + 1e-10);
@@ -627,8 +631,9 @@ __global__ void __launch_bounds__(NTB, DENSE ? 1 : 4) admm_batch_kernel(const __
       bool hit_chk = false, hit_adp = false;
       if (++cnt_chk == a.check_term) { cnt_chk = 0; hit_chk = true; }
       if (++cnt_adp == a.adapt_interval) { cnt_adp = 0; hit_adp = true; }
-      chk_next = hit_chk || last_n;
-      adp_next = !last_n && a.adaptive_rho && hit_adp;
+      tl_stop = time_up;
+      chk_next = hit_chk || last_n || tl_stop;
+      adp_next = !last_n && !tl_stop && a.adaptive_rho && hit_adp;
       const bool full_n = chk_next || adp_next;
       {
         double v[BZ_K];

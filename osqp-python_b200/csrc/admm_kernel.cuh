@@ -319,18 +319,20 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
         }
       }
     }
-    if (full && tid == 0)
+    // the clock is sampled every iteration (upstream osqp_solve does): a check_termination = 0 solve must still stop
+    if (tid == 0)
       v[R_TL] = ((double)(global_timer_ns() - t_start) > a.time_limit_ns) ? 1.0 : 0.0;
     double* bk = bank();
     block_reduce_store<R_K>(v, R_MAXMASK, bk, G, s_red);
     return bk;
   };
 
-  bool time_up = false;
+  bool time_up = false, tl_pending = false;
   auto load_R = [&](const double* bk, bool full) {
     grid_reduce_load<R_K>(bk, G, R_MAXMASK, s_tot);
     rz = s_tot[R_RZ];
     r0max = s_tot[R_R0];
+    time_up = s_tot[R_TL] > 0.5;
     if (full) {
       s_dual = s_tot[R_SDUAL];
       s_ndual = fmax(fmax(s_tot[R_SATY], s_tot[R_SPX]), a.nq_s);
@@ -341,7 +343,6 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
       gap = obj - dobj;
       ndx = s_tot[R_NDX];
       qdx = s_tot[R_QDX];
-      time_up = s_tot[R_TL] > 0.5;
       prim_res = t_prim;
       nprim = fmax(t_ax, t_z);
     }
@@ -396,8 +397,9 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
   // ================================================================== main loop
   for (;;) {
     const bool last = (k >= a.max_iter);
-    const bool chk = k > 0 && ((a.check_term > 0 && (k % a.check_term) == 0) || last);
-    const bool adp = k > 0 && !last && a.adaptive_rho && a.adapt_interval > 0 && (k % a.adapt_interval) == 0;
+    const bool tlp = tl_pending;      // the clock ran out during the previous iteration: evaluate this iterate, then stop
+    const bool chk = k > 0 && ((a.check_term > 0 && (k % a.check_term) == 0) || last || tlp);
+    const bool adp = k > 0 && !last && !tlp && a.adaptive_rho && a.adapt_interval > 0 && (k % a.adapt_interval) == 0;
     const bool full = chk || adp;
 
     {
@@ -406,7 +408,8 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
       load_R(bk, full);
       mark(0);
     }
-    if (full && a.verbose && cta == 0 && tid == 0 && chk) {
+    if (time_up) tl_pending = true;
+    if (full && a.verbose && cta == 0 && tid == 0 && chk && !tlp) {
       const int row = (k / (a.check_term > 0 ? a.check_term : 1)) - 1;
       if (row >= 0 && row < a.log_cap) {
         a.log[row] = LogRow{k, 0, obj, prim_res, dual_res, rho, (double)(global_timer_ns() - t_start) * 1e-6};
@@ -424,8 +427,8 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
         if (!status) status = 7;  // MAX_ITER_REACHED
         break;
       }
-      if (time_up) { status = 8; break; }
     }
+    if (tlp) { status = 8; break; }   // TIME_LIMIT_REACHED, with the residuals of the returned iterate
     if (adp) {
       // reference: _osqp.py:880-930 (scaled quantities)
       const double pr = s_prim / (s_nprim + 1e-10);
@@ -560,7 +563,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel(const __grid_constant__ KAr
     // ---------------------------------------------------------------- Z phase
     const int kn = k + 1;
     const bool last_n = (kn >= a.max_iter);
-    const bool full_n = ((a.check_term > 0 && (kn % a.check_term) == 0) || last_n) ||
+    const bool full_n = ((a.check_term > 0 && (kn % a.check_term) == 0) || last_n || tl_pending) ||
                         (!last_n && a.adaptive_rho && a.adapt_interval > 0 && (kn % a.adapt_interval) == 0);
     {
       double v[Z_K];

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
   double t_prim = 0, t_ax = 0, t_z = 0;
   double ndx = 0, qdx = 0;
   double rz = 0, r0max = 0;
-  bool time_up = false;
+  bool time_up = false, tl_pending = false;
 
   auto bank = [&]() -> double* { return a.red + (size_t)(sync.epoch & 1ULL) * KMAX * G; };
 
@@ -317,13 +317,14 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
         }
       }
     }
-    if (full && tid == 0)
+    if (tid == 0)   // every iteration (see admm_kernel.cuh)
       v[R_TL] = ((double)(global_timer_ns() - t_start) > a.time_limit_ns) ? 1.0 : 0.0;
     double* bk = bank();
     block_reduce_store<R_K>(v, R_MAXMASK, bk, G, s_red);
     if (!xs.template barrier_x<R_K>(bk, R_MAXMASK, s_tot)) return false;
     rz = s_tot[R_RZ];
     r0max = s_tot[R_R0];
+    time_up = s_tot[R_TL] > 0.5;
     if (full) {
       s_dual = s_tot[R_SDUAL];
       s_ndual = fmax(fmax(s_tot[R_SATY], s_tot[R_SPX]), a.nq_s);
@@ -334,7 +335,6 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
       gap = obj - dobj;
       ndx = s_tot[R_NDX];
       qdx = s_tot[R_QDX];
-      time_up = s_tot[R_TL] > 0.5;
       prim_res = t_prim;
       nprim = fmax(t_ax, t_z);
     }
@@ -390,13 +390,15 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
   // ================================================================== main loop
   for (;;) {
     const bool last = (k >= a.max_iter);
-    const bool chk = k > 0 && ((a.check_term > 0 && (k % a.check_term) == 0) || last);
-    const bool adp = k > 0 && !last && a.adaptive_rho && a.adapt_interval > 0 && (k % a.adapt_interval) == 0;
+    const bool tlp = tl_pending;
+    const bool chk = k > 0 && ((a.check_term > 0 && (k % a.check_term) == 0) || last || tlp);
+    const bool adp = k > 0 && !last && !tlp && a.adaptive_rho && a.adapt_interval > 0 && (k % a.adapt_interval) == 0;
     const bool full = chk || adp;
 
     if (!phase_R(full, false)) B200QP_DIE();
     mark(0);
-    if (full && a.verbose && cta == 0 && tid == 0 && chk && rank == 0) {
+    if (time_up) tl_pending = true;
+    if (full && a.verbose && cta == 0 && tid == 0 && chk && !tlp && rank == 0) {
       const int row = (k / (a.check_term > 0 ? a.check_term : 1)) - 1;
       if (row >= 0 && row < a.log_cap) {
         a.log[row] = LogRow{k, 0, obj, prim_res, dual_res, rho, (double)(global_timer_ns() - t_start) * 1e-6};
@@ -414,8 +416,8 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
         if (!status) status = 7;
         break;
       }
-      if (time_up) { status = 8; break; }
     }
+    if (tlp) { status = 8; break; }
     if (adp) {
       const double pr = s_prim / (s_nprim + 1e-10);
       const double du = s_dual / (s_ndual + 1e-10);
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(NT, 2) admm_kernel_dist(const __grid_constant_
     // ---------------------------------------------------------------- Z phase (my rows)
     const int kn = k + 1;
     const bool last_n = (kn >= a.max_iter);
-    const bool full_n = ((a.check_term > 0 && (kn % a.check_term) == 0) || last_n) ||
+    const bool full_n = ((a.check_term > 0 && (kn % a.check_term) == 0) || last_n || tl_pending) ||
                         (!last_n && a.adaptive_rho && a.adapt_interval > 0 && (kn % a.adapt_interval) == 0);
     {
       double v[Z_K];

@@ -96,6 +96,13 @@ __global__ void k_absmax_sum_final(int nblocks, const double* __restrict__ part,
   }
 }
 
+// values of a scaled CSR matrix -> their slots in the compacted-slice tile blob (csl_host.h)
+__global__ void k_csl_pack(int cnt, const int* __restrict__ src, const unsigned* __restrict__ dst,
+                           const double* __restrict__ val, double* __restrict__ blob) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < cnt) blob[dst[e]] = val[src[e]];
+}
+
 // ---- rho vector / constraint typing (reference: _osqp.py:499-562) -------------------------------
 __global__ void k_type_and_rho(int m, const double* __restrict__ l, const double* __restrict__ u, double rho,
                                int rho_is_vec, double eq_factor, int* __restrict__ ctype, double* __restrict__ rho_v,

@@ -18,8 +18,10 @@
 #include <vector>
 
 #include "admm_kernel.cuh"
+#include "csl_args.h"
 #include "admm_kernel_dist.cuh"
 #include "aux_kernels.cuh"
+#include "csl_host.h"
 #include "internal_view.h"
 #include "spmv_kernels.cuh"
 #include "tiling.h"
@@ -166,6 +168,17 @@ struct Work {
     unsigned long long xepoch = 0;
     bool broken = false;
   } dist;
+  // ---- compacted-slice tiles + TMA ring kernel (admm_kernel_csl.cuh); enabled when every tile fits a ring stage
+  struct Csl {
+    bool enabled = false;
+    DBuf<unsigned> toffN, toffM, dstN1, dstN2, dstM;
+    DBuf<unsigned char> blobN, blobM;
+    DBuf<int> srcN1, srcN2, srcM, part_tn, part_tm;
+    DBuf<long long> cta_ns;      // B200QP_DEBUG_CTA=1: per-CTA work time of the B / C phases
+    int ntilesN = 0, ntilesM = 0, S = 0, capb = 0, G = 1, un = 4, um = 4;
+    size_t smem = 0;
+    double tile_bytes = 0;       // blob bytes of N + M (the byte model of the CSL kernel)
+  } csl;
   bool in_flight = false;
   double t_solve_begin = 0;
   double *h_x = nullptr, *h_y = nullptr, *h_pc = nullptr, *h_dc = nullptr;  // pinned
@@ -181,6 +194,8 @@ struct Work {
       b->free();
     pol_ctype.free(); pol_count.free(); adj_q.free(); adj_act.free();
     ctype.free(); stage_i.free(); part_n.free(); part_m.free(); ctrl.free(); out.free(); log.free();
+    csl.toffN.free(); csl.toffM.free(); csl.dstN1.free(); csl.dstN2.free(); csl.dstM.free(); csl.blobN.free(); csl.blobM.free();
+    csl.srcN1.free(); csl.srcN2.free(); csl.srcM.free(); csl.part_tn.free(); csl.part_tm.free(); csl.cta_ns.free();
     for (int h = 0; h < MAXW; ++h)
       if (dist.opened[h] && dist.peer[h]) cudaIpcCloseMemHandle(dist.peer[h]);
     if (dist.region) cudaFree(dist.region);
@@ -211,6 +226,8 @@ struct RegionLayout {
     total = o;
   }
 };
+
+thread_local bool g_skip_csl = false;   // set by b200qp_dist_setup around its call of b200qp_setup (multi-GPU ranks use the CSR kernel)
 
 inline Work* W(b200qp_solver* s) { return static_cast<Work*>(s->work); }
 inline const Work* W(const b200qp_solver* s) { return static_cast<const Work*>(s->work); }
@@ -294,6 +311,28 @@ admm_fn pick_kernel(int lgn, int lgm) {
   CASE(4, 4) CASE(4, 8) CASE(4, 32) CASE(8, 4) CASE(8, 8) CASE(8, 32) CASE(32, 4) CASE(32, 8) CASE(32, 32)
 #undef CASE
   return admm_kernel<8, 8>;
+}
+
+
+// values of the scaled CSR matrices -> their slots in the tile blobs (after equilibration / after a value update)
+void csl_pack_values(Work* w) {
+  if (!w->csl.enabled) return;
+  cudaStream_t s = w->stream;
+  if (w->P.nnz) k_csl_pack<<<cdiv(w->P.nnz, 256), 256, 0, s>>>(w->P.nnz, w->csl.srcN1.p, w->csl.dstN1.p, w->P.val.p, (double*)w->csl.blobN.p);
+  if (w->At.nnz) k_csl_pack<<<cdiv(w->At.nnz, 256), 256, 0, s>>>(w->At.nnz, w->csl.srcN2.p, w->csl.dstN2.p, w->At.val.p, (double*)w->csl.blobN.p);
+  if (w->A.nnz) k_csl_pack<<<cdiv(w->A.nnz, 256), 256, 0, s>>>(w->A.nnz, w->csl.srcM.p, w->csl.dstM.p, w->A.val.p, (double*)w->csl.blobM.p);
+}
+
+CArgs make_cargs(Work* w) {
+  CArgs c{};
+  c.N = CslStream{w->n, w->csl.ntilesN, w->csl.toffN.p, w->csl.blobN.p};
+  c.M = CslStream{w->m, w->csl.ntilesM, w->csl.toffM.p, w->csl.blobM.p};
+  c.part_tn = w->csl.part_tn.p; c.part_tm = w->csl.part_tm.p;
+  c.ps = w->tmp_n.p; c.ss = w->tmp_n2.p;
+  c.S = w->csl.S; c.capb = w->csl.capb;
+  c.cta_ns = w->csl.cta_ns.p;
+  c.direct = std::getenv("B200QP_CSL_DIRECT") ? std::atoi(std::getenv("B200QP_CSL_DIRECT")) : 0;
+  return c;
 }
 
 void set_info_defaults(b200qp_info* info) {
@@ -399,6 +438,18 @@ void launch_admm(b200qp_solver* sv, const KArgs& a) {
     void* params[] = {(void*)&a, (void*)&x};
     CK(cudaEventRecord(w->ev0, w->stream));
     CK(cudaLaunchCooperativeKernel((const void*)fn, dim3(w->dist.G), dim3(NT), params, 0, w->stream));
+  } else if (w->csl.enabled) {
+    KArgs ac = a;
+    ac.G = w->csl.G;
+    if (std::getenv("B200QP_DEBUG_CTA")) {
+      if (!w->csl.cta_ns.p) w->csl.cta_ns.alloc((size_t)2 * w->csl.G);
+      w->csl.cta_ns.zero(w->stream);
+    }
+    CArgs c = make_cargs(w);
+    const void* fn = b200qp_csl_kernel();
+    void* params[] = {(void*)&ac, (void*)&c};
+    CK(cudaEventRecord(w->ev0, w->stream));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(w->csl.G), dim3(CSL_NT), params, w->csl.smem, w->stream));
   } else {
     admm_fn fn = pick_kernel(w->lgn, w->lgm);
     void* params[] = {(void*)&a};
@@ -413,6 +464,16 @@ void finish_admm(b200qp_solver* sv, float* ms) {
   CK(cudaStreamSynchronize(w->stream));
   CK(cudaMemcpy(&w->h_out, w->out.p, sizeof(KOut), cudaMemcpyDeviceToHost));
   CK(cudaEventElapsedTime(ms, w->ev0, w->ev1));
+  if (w->csl.enabled && w->csl.cta_ns.p && !w->dist.connected) {
+    std::vector<long long> h((size_t)2 * w->csl.G);
+    CK(cudaMemcpy(h.data(), w->csl.cta_ns.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int ph = 0; ph < 2; ++ph) {
+      long long mn = h[ph], mx = h[ph]; double sum = 0; int amx = 0;
+      for (int g = 0; g < w->csl.G; ++g) { const long long v = h[2 * g + ph]; if (v < mn) mn = v; if (v > mx) { mx = v; amx = g; } sum += (double)v; }
+      std::fprintf(stderr, "[b200qp] per-CTA work time, phase %s: min %.3f ms, mean %.3f ms, max %.3f ms (CTA %d) over %d CTAs, %lld PCG iterations\n",
+                   ph ? "C" : "B", mn * 1e-6, sum / w->csl.G * 1e-6, mx * 1e-6, amx, w->csl.G, (long long)w->h_out.cg_iters);
+    }
+  }
   if (w->dist.connected) {
     if (w->h_out.aborted || w->h_out.status == 0) w->dist.broken = true;
     else w->dist.xepoch = (unsigned long long)w->h_out.xepoch;
@@ -692,7 +753,56 @@ b200qp_int b200qp_setup(b200qp_solver** solverp, const b200qp_csc* P, const b200
     make_partition(m, w->G, {&w->A.h_ptr}, pm, w->lgm);
     w->part_n.alloc(w->G + 1); w->part_n.upload(pn.data(), w->G + 1, s);
     w->part_m.alloc(w->G + 1); w->part_m.upload(pm.data(), w->G + 1, s);
-    w->red.alloc((size_t)2 * KMAX * w->G); w->red.zero(s);
+    // ---- compacted-slice tiles for the TMA-ring kernel (single-GPU solves; B200QP_FORMAT=csr keeps the CSR kernel)
+    {
+      const char* fmt = std::getenv("B200QP_FORMAT");
+      const bool want = !(fmt && std::string(fmt) == "csr") && !g_skip_csl;
+      CslHost HN, HM;
+      if (want) {
+        csl_build(n, Pp.data(), Pj.data(), Atp.data(), Ati.data(), HN);
+        csl_build(m, Ap.data(), Aj.data(), nullptr, nullptr, HM);
+      }
+      const size_t ring_budget = 100 * 1024;       // per CTA, two CTAs per SM
+      const unsigned capb = ((std::max(HN.max_tile_bytes, HM.max_tile_bytes) + 127u) / 128u) * 128u;
+      const int S = capb ? (int)std::min<size_t>(32, ring_budget / capb) : 0;
+      if (want && HN.ok && HM.ok && S >= CSL_NWC + 2) {
+        Work::Csl& cs = w->csl;
+        cs.S = S; cs.capb = (int)capb; cs.smem = (size_t)S * capb;
+        cs.un = HN.waste5 < HN.waste4 ? 5 : 4;
+        cs.um = HM.waste5 < HM.waste4 ? 5 : 4;
+        if (const char* e = std::getenv("B200QP_CSL_UN")) { const int v = std::atoi(e); if (v == 4 || v == 5) cs.un = v; }
+        if (const char* e = std::getenv("B200QP_CSL_UM")) { const int v = std::atoi(e); if (v == 4 || v == 5) cs.um = v; }
+        const void* fn = b200qp_csl_kernel();
+        // a per-function attribute shared by every solver of the process: always the full budget (a per-solver value
+        // would race between solvers that are set up from different threads)
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_budget));
+        int occ2 = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fn, CSL_NT, cs.smem));
+        if (occ2 >= 1) {
+          const int max_coop = occ2 * prop.multiProcessorCount;
+          long long wantG = ((long long)HN.ntiles + HM.ntiles) / 16;
+          if (const char* e = std::getenv("B200QP_GRID")) wantG = std::atoll(e);
+          cs.G = (int)std::min<long long>(std::max<long long>(wantG, 1), max_coop);
+          cs.ntilesN = HN.ntiles; cs.ntilesM = HM.ntiles;
+          cs.tile_bytes = 16.0 * HN.toff[HN.ntiles] + 16.0 * HM.toff[HM.ntiles];
+          std::vector<int> ptn, ptm;
+          csl_partition(HN, cs.G, ptn);
+          csl_partition(HM, cs.G, ptm);
+          auto up_u = [&](DBuf<unsigned>& d, const std::vector<unsigned>& h) { d.alloc(h.size()); d.upload(h.data(), h.size(), s); };
+          auto up_i = [&](DBuf<int>& d, const std::vector<int>& h) { d.alloc(h.size()); d.upload(h.data(), h.size(), s); };
+          up_u(cs.toffN, HN.toff); up_u(cs.toffM, HM.toff);
+          cs.blobN.alloc(HN.blob.size() + 16); cs.blobN.upload(HN.blob.data(), HN.blob.size(), s);
+          cs.blobM.alloc(HM.blob.size() + 16); cs.blobM.upload(HM.blob.data(), HM.blob.size(), s);
+          up_i(cs.srcN1, HN.src1); up_u(cs.dstN1, HN.dst1); up_i(cs.srcN2, HN.src2); up_u(cs.dstN2, HN.dst2);
+          up_i(cs.srcM, HM.src1); up_u(cs.dstM, HM.dst1);
+          up_i(cs.part_tn, ptn); up_i(cs.part_tm, ptm);
+          CK(cudaStreamSynchronize(s));     // the host vectors die with this scope
+          cs.enabled = true;
+          csl_pack_values(w);
+        }
+      }
+    }
+    w->red.alloc((size_t)2 * KMAX * std::max(w->G, w->csl.G)); w->red.zero(s);
     w->ctrl.alloc(1); w->out.alloc(1);
     w->log_cap = 4096;
     w->log.alloc(w->log_cap);
@@ -706,7 +816,7 @@ b200qp_int b200qp_setup(b200qp_solver** solverp, const b200qp_csc* P, const b200
     sv->solution->prim_inf_cert = w->h_pc; sv->solution->dual_inf_cert = w->h_dc;
     CK(cudaStreamSynchronize(s));
     w->stats.n = n; w->stats.m = m; w->stats.nnzP_full = w->P.nnz; w->stats.nnzA = w->A.nnz;
-    w->stats.grid = w->G; w->stats.block = NT;
+    w->stats.grid = w->csl.enabled ? w->csl.G : w->G; w->stats.block = w->csl.enabled ? CSL_NT : NT;
   } catch (int code) {
     b200qp_cleanup(sv);
     return code;
@@ -979,6 +1089,7 @@ b200qp_int b200qp_update_data_mat(b200qp_solver* solver, const b200qp_float* Px_
       }
     }
     refresh_rho_and_precond(solver, false);                 // Jacobi diagonal follows P and A
+    csl_pack_values(w);
     CK(cudaStreamSynchronize(w->stream));
     solver->info->status_val = B200QP_UNSOLVED;
     std::snprintf(solver->info->status, sizeof(solver->info->status), "%s", "unsolved");
@@ -1188,7 +1299,9 @@ b200qp_int b200qp_dist_setup(b200qp_solver** solverp, b200qp_int rank, b200qp_in
   if (world < 1 || world > MAXW || rank < 0 || rank >= world) return B200QP_DATA_VALIDATION_ERROR;
   b200qp_settings st = *settings;
   if (rank != 0) st.verbose = 0;
+  g_skip_csl = true;
   int err = b200qp_setup(solverp, P, q, A, l, u, m, n, &st);
+  g_skip_csl = false;
   if (err) return err;
   b200qp_solver* sv = *solverp;
   Work* w = W(sv);
