@@ -107,15 +107,20 @@ class Solver {
   }
   b200qp_int warm_start(py::object x, py::object y) {
     darray kx, ky;
-    const b200qp_float* px = opt_doubles(x, kx);
-    const b200qp_float* pyv = opt_doubles(y, ky);
+    py::ssize_t lx = n_, ly = m_;
+    const b200qp_float* px = opt_doubles(x, kx, &lx);
+    const b200qp_float* pyv = opt_doubles(y, ky, &ly);
+    // the C ABI copies n / m doubles from these pointers: a wrong length must not reach it
+    if (lx != n_ || ly != m_) throw py::value_error(std::to_string(B200QP_DATA_VALIDATION_ERROR));
     return b200qp_warm_start(s_, px, pyv);
   }
   b200qp_int update_data_vec(py::object q, py::object l, py::object u) {
     darray kq, kl, ku;
-    const b200qp_float* pq = opt_doubles(q, kq);
-    const b200qp_float* pl = opt_doubles(l, kl);
-    const b200qp_float* pu = opt_doubles(u, ku);
+    py::ssize_t lq = n_, ll = m_, lu = m_;
+    const b200qp_float* pq = opt_doubles(q, kq, &lq);
+    const b200qp_float* pl = opt_doubles(l, kl, &ll);
+    const b200qp_float* pu = opt_doubles(u, ku, &lu);
+    if (lq != n_ || ll != m_ || lu != m_) throw py::value_error(std::to_string(B200QP_DATA_VALIDATION_ERROR));
     return b200qp_update_data_vec(s_, pq, pl, pu);
   }
   b200qp_int update_data_mat(py::object Px, py::object Pi, py::object Ax, py::object Ai) {
