@@ -40,19 +40,36 @@ for p in (ROOT, PKG):
 
 import numpy as np  # noqa: E402
 
+import bench_cpu as CPU  # noqa: E402
+
 METRIC = "admm_iters_per_sec"
 UNIT = "ADMM iters/s"
 N_VARS = int(os.environ.get("B200QP_BENCH_N", 1_000_000))
 N_CONS = int(os.environ.get("B200QP_BENCH_M", N_VARS))
 NNZ_ROW = 10
 SEED = 3
-ENGINE_SPEC = dict(cg_max_iter=100, cg_tol_fraction=0.1, rho_eq_factor=10.0)   # the engine's defaults, for the CPU port
-# dram__bytes_read.sum + dram__bytes_write.sum of one admm_kernel launch of this workload, from the committed
-# `ncu --set full` capture (231.88 GB + 12.23 GB; the n- and m-vectors stay L2-resident, so it is below the
-# algorithmic byte count); only valid for the default problem size
-NCU_TRAFFIC_BYTES = 244.110e9 if (N_VARS, N_CONS) == (1_000_000, 1_000_000) else None
-NCU_TRAFFIC_SOURCE = "profiles/r1d_admm_kernel_ncu_raw.csv (75 ADMM / 642 PCG iterations per launch)"
 SOLVE_KW = dict(eps_abs=1e-3, eps_rel=1e-3, max_iter=4000, warm_starting=False, polishing=False)
+CPU_SAMPLE_ITERS = int(os.environ.get("B200QP_CPU_SAMPLE_ITERS", 10))    # ADMM iterations per CPU sample (both CPU legs)
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the hot kernel on this workload, from the
+    `ncu --set full` capture of the committed build: scripts/ncu_traffic.sh writes profiles/r2_traffic.json next to
+    the raw csv it was read from (a number taken under the profiler is never a bench value; it only sizes the traffic)."""
+    if (N_VARS, N_CONS) != (1_000_000, 1_000_000):
+        return None, "not captured for this problem size"
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        return float(t["dram_bytes_per_launch"]), t["source"]
+    except Exception:      # noqa: BLE001
+        return None, "profiles/r2_traffic.json missing"
+
+
+def config_block():
+    """Identical in both arms (the driver compares it): what is solved, not what was measured."""
+    return {"workload": workload_name(), "n": N_VARS, "m": N_CONS, "nnz_A": N_CONS * NNZ_ROW, "seed": SEED,
+            "settings": dict(SOLVE_KW), "engine_spec": dict(CPU.ENGINE_SPEC),
+            "l2": "inputs larger than L2 (working set ~0.45 GB vs 126 MB L2); no flush between steps"}
 
 
 def workload_name():
@@ -130,77 +147,70 @@ def dist_env():
 # ----------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference's CPU implementation of the path on the host cores.  The reference's compiled solver
-    (osqp v1.0.0 / QDLDL) is not vendored and osqppurepy cannot travel to the GPU box, so this is the
-    oracle port of it; direct factorisation cannot finish at n = m = 1e6 on random sparsity,
-    hence the engine-spec PCG mode.  One step = one ADMM iteration (bounded sample), continuing the solve."""
+    (osqp v1.0.0 / QDLDL) is not vendored and osqppurepy cannot travel to the GPU box, so this is the oracle port of
+    it (`kind: "port"`, not the upstream C solver); a direct factorisation cannot finish at n = m = 1e6 on random
+    sparsity, hence the engine-spec PCG mode.  One step = one bounded sample: the first CPU_SAMPLE_ITERS
+    ADMM iterations of the cold-start solve in ONE solve() call (no per-call overhead per iteration), on every host
+    thread (torchrun's OMP_NUM_THREADS=1 is overridden)."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    from oracle.osqp_oracle import OracleSolver
+    threads = CPU.use_all_host_threads()
     P, q, A, l, u = make_problem()
-    kw = dict(SOLVE_KW)
-    kw.pop("warm_starting"); kw.pop("polishing")
-    s = OracleSolver(P, q, A, l, u, linsys="indirect", warm_starting=1, check_termination=0,
-                     adaptive_rho=0, **ENGINE_SPEC, **kw)
-    cap_s = float(os.environ.get("B200QP_REF_BUDGET_S", 150))
+    budget = float(os.environ.get("B200QP_REF_BUDGET_S", 240))
     t_begin = time.perf_counter()
-    s.s.max_iter = 1
     done_w = 0
-    for _ in range(args.warmup):
-        if time.perf_counter() - t_begin > cap_s / 3:
-            break
-        s.solve(); done_w += 1
-    t0 = time.perf_counter()
-    iters, cg = 0, 0
+    for _ in range(min(args.warmup, 1)):                       # one short warm-up sample (page-in, OpenMP pool)
+        CPU.config4_sample(P, q, A, l, u, SOLVE_KW, 2)
+        done_w += 1
+    iters = cg = steps = 0
+    dt = 0.0
+    used = threads
     for _ in range(args.steps):
-        if time.perf_counter() - t_begin > cap_s:
+        if steps and time.perf_counter() - t_begin + dt / steps > budget:
             break
-        r = s.solve()
-        iters += 1; cg += r.info.cg_iters
-    dt = time.perf_counter() - t0
-    val = iters / dt if dt > 0 and iters else 0.0
-    from oracle import osqp_oracle
-    cores = osqp_oracle.host_threads()
-    sample = (f"{iters} ADMM iterations ({cg} PCG iterations) of the same problem after {done_w} warm-up "
-              f"iterations; CSR SpMV on {cores} thread(s) (OpenMP helper if faster than scipy on this host) + numpy, "
-              f"{os.cpu_count()} host cores")
+        k, c, t, used = CPU.config4_sample(P, q, A, l, u, SOLVE_KW, CPU_SAMPLE_ITERS)
+        iters += k; cg += c; dt += t; steps += 1
+    val = iters / dt if dt > 0 else 0.0
+    sample = (f"{steps} sample(s) of the first {CPU_SAMPLE_ITERS} ADMM iterations of the cold-start solve ({cg / max(iters, 1):.1f} PCG "
+              f"iterations each, {dt:.1f} s in total), one solve() call per sample; oracle port, CSR SpMV on {used} thread(s) "
+              f"(OpenMP helper when faster than scipy's csr_matvec on this host) + numpy; {CPU.host_cores()} host cores available")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": iters, "warmup": done_w, "ms_per_step": 1e3 * dt / max(iters, 1), "higher_is_better": True,
+            "steps": steps, "warmup": done_w, "ms_per_step": 1e3 * dt / max(steps, 1), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(), "note": "step = 1 ADMM iteration of the CPU port (bounded sample)"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": config_block(),
+            "detail": {"step": f"{CPU_SAMPLE_ITERS} ADMM iterations of the CPU port (bounded sample)",
+                       "pcg_iters_per_admm_iter": cg / max(iters, 1)},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------- our arm
-def cpu_baseline_sample(P, q, A, l, u, budget_iters=3):
-    from oracle.osqp_oracle import OracleSolver
-    kw = dict(SOLVE_KW)
-    kw.pop("warm_starting"); kw.pop("polishing")
-    kw["max_iter"] = budget_iters
-    s = OracleSolver(P, q, A, l, u, linsys="indirect", check_termination=0, adaptive_rho=0, **ENGINE_SPEC, **kw)
-    t0 = time.perf_counter()
-    r = s.solve()
-    dt = time.perf_counter() - t0
-    from oracle import osqp_oracle
-    cores = osqp_oracle.host_threads()
-    return {"value": budget_iters / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {budget_iters} ADMM iterations ({r.info.cg_iters} PCG iterations, {dt:.1f} s) of the same "
-                      f"cold-start solve; oracle port, CSR SpMV on {cores} thread(s) (OpenMP helper if faster than scipy "
-                      f"on this host) + numpy, {os.cpu_count()} host cores",
-            "pcg_iters_per_admm_iter": r.info.cg_iters / budget_iters}
+def cpu_baseline_sample(P, q, A, l, u):
+    """Same sampling rule as the reference arm: the first CPU_SAMPLE_ITERS ADMM iterations, one solve() call."""
+    k, cg, dt, used = CPU.config4_sample(P, q, A, l, u, SOLVE_KW, CPU_SAMPLE_ITERS)
+    return {"value": k / dt, "unit": UNIT, "cores": used, "kind": "port",
+            "sample": f"first {k} ADMM iterations ({cg} PCG iterations, {dt:.1f} s) of the same cold-start solve, one solve() call; "
+                      f"oracle port, CSR SpMV on {used} thread(s) (OpenMP helper when faster than scipy on this host) + numpy; "
+                      f"{CPU.host_cores()} host cores available",
+            "pcg_iters_per_admm_iter": cg / max(k, 1)}
 
 
 def spmv_line(A, peak):
-    """Standalone per-iteration SpMV (y = A x) achieved GB/s, every variant, L2 flushed between launches."""
+    """Standalone per-iteration SpMV (y = A x) achieved GB/s, every variant; "flushed" = a buffer larger than L2 is READ
+    between launches and x is brought back (inside the solver the gathered vector was just written, the matrix is not in
+    L2); "tile-tma" is the scheme of the persistent kernel's phases."""
     from b200qp import lowlevel
     M = A.tocsr()
     plan = lowlevel.SpmvPlan(M)
     x = np.random.default_rng(7).standard_normal(M.shape[1])
     out = {}
     for v, name in enumerate(lowlevel.variants()):
-        plan.run(x, variant=v, reps=3, want_y=False)
+        try:
+            plan.run(x, variant=v, reps=3, want_y=False)
+        except RuntimeError:          # the tile variant refuses matrices it cannot hold (rows > 255 entries)
+            continue
         _, ms_cold = plan.run(None, variant=v, reps=10, flush_l2=True, want_y=False)
         _, ms_warm = plan.run(None, variant=v, reps=20, flush_l2=False, want_y=False)
         out[name] = {"ms_flushed": ms_cold, "gbs_flushed": plan.algo_bytes() / ms_cold / 1e6,
@@ -264,7 +274,7 @@ def run_ours(args):
         prob.solve()
     sampler = ClockSampler(gpu=local)
     sampler.start()
-    dev_ms, wall_ms, iters, cg, bytes_algo, launches = 0.0, 0.0, 0, 0, 0.0, 0
+    dev_ms, wall_ms, iters, cg, bytes_algo, bytes_engine, launches = 0.0, 0.0, 0, 0, 0.0, 0.0, 0
     status = None
     phases = [0.0] * 8
     for i in range(args.steps):
@@ -274,6 +284,7 @@ def run_ours(args):
         wall_ms += 1e3 * (time.perf_counter() - t0)
         st = prob.stats()
         dev_ms += st["kernel_ms"]; iters += st["admm_iters"]; cg += st["cg_iters"]; bytes_algo += st["algo_bytes"]
+        bytes_engine += st["algo_bytes_engine"]
         phases = [a + b for a, b in zip(phases, st["phase_ms"])]
         launches += 1 + 3 + 2                        # ADMM kernel; q-update (scale + 2 norm kernels); store x / y
         status = res.info.status
@@ -281,22 +292,41 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     value = iters / (dev_ms * 1e-3)
     achieved = bytes_algo / (dev_ms * 1e-3) / 1e9
+    achieved_engine = bytes_engine / (dev_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic()
+    tile = st["kernel_kind"] == 1
+    names = ["R", "B_Au", "C_Ku", "V_axpy_dots", "x4", "Z", "x6", "x7"] if tile else ["R", "C1_Ap", "C2_Kp", "C3_axpy_dots", "C4_p", "Z", "x6", "x7"]
+    kernel = ("b200qp::admm_kernel_csl (persistent; compacted-slice tiles streamed by cp.async.bulk into an mbarrier ring, "
+              "one launch per solve)") if tile else "b200qp::admm_kernel (persistent CSR lanes-per-row kernel, one launch per solve)"
+    # the per-iteration SpMV the metric names: in-kernel phase time per PCG iteration (CTA 0's clock, barrier wait included)
+    # against the algorithmic bytes of one product
+    def phase_roof(ms_total, nbytes):
+        us = 1e3 * ms_total / max(cg, 1)
+        gbs = nbytes / (us * 1e-6) / 1e9 if us > 0 else 0.0
+        return {"us_per_product": us, "algo_bytes": nbytes, "achieved": gbs, "unit": "GB/s", "frac": gbs / peak,
+                "frac_of_8TBs": gbs / 8000.0}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(), "admm_iters_per_step": iters // args.steps,
-                   "pcg_iters_per_admm_iter": cg / max(iters, 1), "status": status, "l2": "inputs larger than L2 "
-                   "(working set ~0.45 GB vs 126 MB L2); no flush between steps",
-                   "phase_ms_per_step": dict(zip(["R", "C1_Ap", "C2_Kp", "C3_axpy_dots", "C4_p", "Z", "x6", "x7"],
-                                                 [round(v / args.steps, 3) for v in phases])),
-                   "grid": f"{st['grid']}x{st['block']}", "setup_s": t_setup, "problem_gen_s": t_gen,
-                   "settings": {k: v for k, v in SOLVE_KW.items()}},
-        "roofline": {"bound": "hbm", "kernel": "b200qp::admm_kernel (persistent, one launch per solve)",
+        "config": config_block(),
+        "detail": {"admm_iters_per_step": iters // args.steps, "pcg_iters_per_admm_iter": cg / max(iters, 1), "status": status,
+                   "phase_ms_per_step": dict(zip(names, [round(v / args.steps, 3) for v in phases])),
+                   "grid": f"{st['grid']}x{st['block']}", "ring": f"{st['ring_stages']} stages x {st['ring_stage_bytes']} B" if tile else None,
+                   "setup_s": t_setup, "problem_gen_s": t_gen},
+        "roofline": {"bound": "hbm", "kernel": kernel,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "frac_of_8TBs": achieved / 8000.0, "peak_source": peak_src, "traffic": NCU_TRAFFIC_BYTES,
-                     "traffic_source": NCU_TRAFFIC_SOURCE,
-                     "algo_bytes_per_launch": bytes_algo / args.steps, "ms_per_launch": dev_ms / args.steps},
+                     "frac_of_8TBs": achieved / 8000.0, "peak_source": peak_src,
+                     "byte_model": "SURVEY.md 8(d): per PCG iteration B(P)+B(A)+B(A')+64n, per ADMM iteration B(A')+B(A)+8(5n+10m), "
+                                   "per check B(P)+B(A'); B(M) = 12 nnz + 4(rows+1) + 8 rows + 8 cols",
+                     "algo_bytes_per_launch": bytes_algo / args.steps, "ms_per_launch": dev_ms / args.steps,
+                     "engine_model": {"achieved": achieved_engine, "frac": achieved_engine / peak,
+                                      "algo_bytes_per_launch": bytes_engine / args.steps,
+                                      "what": "the kernel's own storage and vector passes (tile blobs, V phase 7 reads + 5 writes)"},
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "per_iteration_spmv": {"A_u": phase_roof(phases[1], st["spmv_bytes_A"]),
+                                            "K_u": phase_roof(phases[2], st["spmv_bytes_K"]),
+                                            "note": "phase time on CTA 0 incl. the grid barrier, per PCG iteration; K u = P u + sigma u + A' t"}},
         "e2e": {"value": iters / (wall_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n,
                 "d2h_bytes_per_step": 16 * (n + m) + 128, "ms_per_step": wall_ms / args.steps,
                 "api": "osqp.OSQP.update(q=host) + solve() -> res.x, res.y on host"},
@@ -318,7 +348,8 @@ def run_ours(args):
             line["gpu_launches"] += 5
     if not args.no_batch:
         from b200qp import batchbench
-        if guarded("batch", lambda: batchbench.batch_line(args, with_cpu=not args.no_cpu_baseline)):
+        cpu_fn = None if args.no_cpu_baseline else CPU.mpc_batch_sample
+        if guarded("batch", lambda: batchbench.batch_line(args, cpu_sample=cpu_fn)):
             line["gpu_launches"] += args.steps * line["batch"]["gpu_launches_per_step"]
     if not args.no_cpu_baseline:
         if not guarded("cpu_baseline", lambda: cpu_baseline_sample(P, q, A, l, u)):

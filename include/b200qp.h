@@ -177,7 +177,12 @@ typedef struct {
   double algo_bytes;      /* algorithmic HBM bytes of that launch (DESIGN.md byte model) */
   b200qp_int grid, block; /* launch shape                                               */
   b200qp_int n, m, nnzP_full, nnzA;
-  double phase_ms[8];     /* device time per phase kind (R, C1, C2, C3, C4, Z, -, -), measured on CTA 0 */
+  double phase_ms[8];     /* device time per phase kind, measured on CTA 0 (barrier waits included):
+                             CSR kernel R, C1 (A p), C2 (K p), C3, C4, Z; tile kernel R, B (A u), C (K u), V, -, Z */
+  double algo_bytes_engine; /* same launch, counted with the engine's own storage (tile blobs, its vector passes) */
+  double spmv_bytes[2];   /* algorithmic bytes of ONE A-product phase / ONE K-product phase (SURVEY 8d model)  */
+  b200qp_int kernel_kind; /* 0 = CSR lanes-per-row kernel, 1 = compacted-slice tiles + TMA ring, 2 = multi-GPU */
+  b200qp_int ring_stages, ring_stage_bytes;
 } b200qp_stats;
 
 /* ---- the reference path ------------------------------------------------------------------ */

@@ -97,6 +97,8 @@ class Settings:
     delta: float = 1e-6
     polish_refine_iter: int = 3
     time_limit: float = 1e10
+    # upstream v1.0 addition (no counterpart in osqppurepy): also require |obj - dual_obj| < eps_abs + eps_rel max(|obj|, |dual_obj|)
+    check_dualgap: int = 0
     # indirect mode (engine spec)
     cg_max_iter: int = 100
     cg_tol_fraction: float = 0.1
@@ -122,6 +124,9 @@ def _omp_lib():
             lib.oracle_csr_matvec.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 5
             lib.oracle_csr_matvec.restype = None
             lib.oracle_omp_threads.restype = ctypes.c_int
+            if hasattr(lib, "oracle_set_threads"):
+                lib.oracle_set_threads.argtypes = [ctypes.c_int]
+                lib.oracle_set_threads.restype = None
             _OMP = lib
         except OSError:
             _OMP = False
@@ -241,7 +246,7 @@ class OracleSolver:
         self.x, self.z, self.y = np.zeros(n), np.zeros(m), np.zeros(m)
         self.dx, self.dy = np.zeros(n), np.zeros(m)
         self.info = SimpleNamespace(iter=0, status_val=UNSOLVED, status="unsolved", status_polish=0,
-                                    obj_val=0.0, prim_res=0.0, dual_res=0.0, rho_updates=0,
+                                    obj_val=0.0, dual_obj_val=0.0, duality_gap=0.0, prim_res=0.0, dual_res=0.0, rho_updates=0,
                                     rho_estimate=self.s.rho, setup_time=time.perf_counter() - t0,
                                     solve_time=0.0, polish_time=0.0, cg_iters=0)
 
@@ -385,6 +390,16 @@ class OracleSolver:
         r.dual = cinv * nrm(Dinv * (px + self.q + aty))                         # ref:753-764
         r.prim_norm = max(nrm(Einv * ax), nrm(Einv * z))                        # ref:728-751
         r.dual_norm = cinv * max(nrm(Dinv * aty), nrm(Dinv * px), nrm(Dinv * self.q))  # ref:766-794
+        # Dual objective and duality gap.  osqppurepy has neither; the binding exposes them (bindings.cpp.in:479,482:
+        # dual_obj_val, duality_gap) and upstream v1.0 tests |gap| when check_dualgap is set.  Lagrange dual of the QP:
+        #   d(y) = -1/2 x'Px - sup_{l <= z <= u} y'z = -1/2 x'Px - (u'y+ + l'y-)    (finite bounds only; the scaled
+        # y, l, u carry c E^-1, E, E, so the products divide by c like the objective).  No reference file pins the
+        # numbers; tests check them against this formula, against strong duality at an optimum, and GPU vs oracle.
+        fin_u, fin_l = self.u < INF_THRESH, self.l > -INF_THRESH
+        sup = float(np.sum(np.where(fin_u, self.u * np.maximum(y, 0), 0.0)) + np.sum(np.where(fin_l, self.l * np.minimum(y, 0), 0.0))) \
+            if self.m else 0.0
+        r.dual_obj = (-0.5 * float(x @ px) - sup) / self.c
+        r.gap = r.obj - r.dual_obj
         # scaled quantities for the rho estimate (ref:880-908)
         r.s_prim, r.s_prim_norm = nrm(ax - z), max(nrm(ax), nrm(z))
         r.s_dual, r.s_dual_norm = nrm(px + self.q + aty), max(nrm(aty), nrm(px), nrm(self.q))
@@ -437,7 +452,8 @@ class OracleSolver:
             return NON_CVX
         prim_ok = self.m == 0 or r.prim < f * s.eps_abs + f * s.eps_rel * r.prim_norm
         dual_ok = r.dual < f * s.eps_abs + f * s.eps_rel * r.dual_norm
-        if prim_ok and dual_ok:
+        gap_ok = (not s.check_dualgap) or abs(r.gap) < f * s.eps_abs + f * s.eps_rel * max(abs(r.obj), abs(r.dual_obj))
+        if prim_ok and dual_ok and gap_ok:
             return SOLVED_INACCURATE if approximate else SOLVED
         if not prim_ok and self._primal_infeasible(f * s.eps_prim_inf):
             return PRIMAL_INFEASIBLE_INACCURATE if approximate else PRIMAL_INFEASIBLE
@@ -492,12 +508,15 @@ class OracleSolver:
             status = self._check(r, approximate=True) or MAX_ITER_REACHED         # ref:1263-1266
         info.iter, info.status_val, info.status = k, status, STATUS_NAME[status]
         info.obj_val, info.prim_res, info.dual_res = r.obj, r.prim, r.dual
+        info.dual_obj_val, info.duality_gap = r.dual_obj, r.gap
         if status in (PRIMAL_INFEASIBLE, PRIMAL_INFEASIBLE_INACCURATE):
-            info.obj_val = INFTY
+            info.obj_val = info.dual_obj_val = INFTY
+            info.duality_gap = np.nan
         elif status in (DUAL_INFEASIBLE, DUAL_INFEASIBLE_INACCURATE):
-            info.obj_val = -INFTY
+            info.obj_val = info.dual_obj_val = -INFTY
+            info.duality_gap = np.nan
         elif status == NON_CVX:
-            info.obj_val = np.nan
+            info.obj_val = info.dual_obj_val = info.duality_gap = np.nan
         info.rho_estimate = self._rho_estimate(r)
         info.solve_time = time.perf_counter() - t0
         if s.polishing and status == SOLVED:
@@ -552,6 +571,7 @@ class OracleSolver:
         if ok:
             self.x, self.z, self.y = px, pz, py
             self.info.obj_val, self.info.prim_res, self.info.dual_res = rp.obj, rp.prim, rp.dual
+            self.info.dual_obj_val, self.info.duality_gap = rp.dual_obj, rp.gap
             self.info.status_polish = 1
         else:
             self.info.status_polish = -1

@@ -19,3 +19,4 @@ void oracle_csr_matvec(int rows, const int* ptr, const int* idx, const double* v
 }
 
 int oracle_omp_threads(void) { return omp_get_max_threads(); }
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }

@@ -29,59 +29,9 @@ def reduce_counts(dev_ms, wall_ms, counts, dist=None, torch=None, device=None):
     return float(t[0]), float(t[1]), c.cpu().numpy()
 
 
-def _cpu_worker(job):
-    """One host process: the reference's way on one core -- one setup, then update(l, u) + cold solve per QP (oracle
-    port of the reference algorithm, direct KKT factorisation as in its qdldl path).  Returns (QPs, iterations, seconds)."""
-    import os as _os
-    import sys as _sys
-    root = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
-    for p_ in (root, _os.path.join(root, "osqp-python_b200")):
-        if p_ not in _sys.path:
-            _sys.path.insert(0, p_)
-    from oracle.osqp_oracle import OracleSolver
-    P, q, A, l, u = job
-    s = OracleSolver(P, q, A, l[0], u[0], linsys="direct", **{k: v for k, v in KW.items() if k != "warm_starting"})
-    t0 = time.perf_counter()
-    iters = 0
-    for b in range(len(l)):
-        s.update(l=l[b], u=u[b])
-        s.x[:] = 0; s.z[:] = 0; s.y[:] = 0
-        s.update_rho(0.1)
-        iters += s.solve().info.iter
-    return len(l), iters, time.perf_counter() - t0
-
-
-def cpu_sample(P, q, A, l, u, per_proc=16, procs=None):
-    """CPU baseline of config 5 on the host cores: independent QPs are spread over one process per core (spawned:
-    the parent holds a CUDA context), each running the oracle port; throughput = QPs / slowest worker's solve time.
-    Falls back to one core if the pool cannot be used."""
-    procs = procs or min(os.cpu_count() or 1, 32)
-    jobs = [(P, q, A, l[i * per_proc:(i + 1) * per_proc], u[i * per_proc:(i + 1) * per_proc]) for i in range(procs)]
-    jobs = [j for j in jobs if len(j[3])]
-    used, res = 1, None
-    if len(jobs) > 1:
-        try:
-            import multiprocessing as mp
-            from concurrent.futures import ProcessPoolExecutor
-            # an executor, not a Pool: a child that dies raises BrokenProcessPool here instead of being respawned
-            with ProcessPoolExecutor(len(jobs), mp_context=mp.get_context("spawn")) as pool:
-                res = list(pool.map(_cpu_worker, jobs, timeout=120))
-            used = len(jobs)
-        except Exception:      # noqa: BLE001
-            res = None
-    if res is None:
-        res = [_cpu_worker(jobs[0])]
-        used = 1
-    count = sum(r[0] for r in res)
-    iters = sum(r[1] for r in res)
-    dt = max(r[2] for r in res)
-    return {"value": count / dt, "unit": "QPs/s", "cores": used, "kind": "port",
-            "sample": f"{count} of the {BATCH} QPs ({iters} ADMM iterations, slowest worker {dt:.2f} s) on {used} host process(es), "
-                      f"{per_proc} QPs each: one setup, update(l,u) + cold solve per QP; oracle port, sparse LU of the KKT "
-                      f"matrix; {os.cpu_count()} host cores"}
-
-
-def batch_line(args, rank=0, world=1, local=0, dist=None, torch=None, with_cpu=True):
+def batch_line(args, rank=0, world=1, local=0, dist=None, torch=None, cpu_sample=None):
+    """cpu_sample: optional callable (P, q, A, l, u, KW, BATCH) -> cpu_baseline dict, supplied by bench.py (the CPU leg
+    lives outside the package: nothing here imports the oracle)."""
     import osqp
     from b200qp import problems
     lo, hi = shard_range(BATCH, rank, world)
@@ -137,8 +87,8 @@ def batch_line(args, rank=0, world=1, local=0, dist=None, torch=None, with_cpu=T
         "note": "latency-bound, not HBM-bound: per QP the kernel reads 16m + 8n bytes and writes 16(n+m) bytes once; "
                 f"the shared matrices ({12 * nnz} bytes) stay in L1",
     }
-    if with_cpu and rank == 0:
-        line["cpu_baseline"] = cpu_sample(P, q, A, l_all, u_all)        # all host cores
+    if cpu_sample is not None and rank == 0:
+        line["cpu_baseline"] = cpu_sample(P, q, A, l_all, u_all, KW, BATCH)        # all host cores
     return line
 
 

@@ -174,7 +174,7 @@ def bench(args, rank, world, local, B):
     batch = None
     if not getattr(args, "no_batch", False):
         from b200qp import batchbench
-        batch = batchbench.batch_line(args, rank, world, local, dist=dist, torch=torch, with_cpu=False)
+        batch = batchbench.batch_line(args, rank, world, local, dist=dist, torch=torch)
     if rank == 0:
         peak, peak_src = B.measured_peak()
         achieved = bytes_algo / (dev_ms * 1e-3) / 1e9      # whole-job algorithmic bytes (same model as N = 1)
@@ -182,14 +182,14 @@ def bench(args, rank, world, local, B):
             "metric": B.METRIC, "value": iters / (dev_ms * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": B.workload_name(), "admm_iters_per_step": iters // args.steps,
+            "config": B.config_block(),
+            "detail": {"admm_iters_per_step": iters // args.steps,
                        "pcg_iters_per_admm_iter": cg / max(iters, 1), "status": res.info.status,
                        "partition": f"{world} row slabs of A + {world} variable slices of P and A'; p, d, w, w2 all-gathered by "
                                     "NVLink stores fused into the producing phases of the persistent kernel, x replicated",
                        "phase_ms_per_step_rank0": dict(zip(["R_slice_push_u", "B_Au_push_t", "C_Ku_slice", "V_slice_push_u", "x4", "Z_push_w2",
                                                             "gather_d", "x7"], [round(v / args.steps, 3) for v in phases])),
-                       "l2": "inputs larger than L2; no flush between steps", "grid": f"{st['grid']}x{st['block']} per GPU",
-                       "setup_s": t_setup, "settings": dict(B.SOLVE_KW)},
+                       "grid": f"{st['grid']}x{st['block']} per GPU", "setup_s": t_setup},
             "roofline": {"bound": "hbm", "kernel": "b200qp::admm_kernel_dist (persistent, one launch per rank per solve)",
                          "achieved": achieved / world, "peak": peak, "unit": "GB/s", "frac": achieved / world / peak,
                          "peak_source": peak_src, "traffic": None,

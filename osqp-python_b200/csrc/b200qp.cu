@@ -177,7 +177,7 @@ struct Work {
     DBuf<long long> cta_ns;      // B200QP_DEBUG_CTA=1: per-CTA work time of the B / C phases
     int ntilesN = 0, ntilesM = 0, S = 0, capb = 0, G = 1, un = 4, um = 4;
     size_t smem = 0;
-    double tile_bytes = 0;       // blob bytes of N + M (the byte model of the CSL kernel)
+    double bytesN = 0, bytesM = 0;   // blob bytes of the two tile streams (engine byte model)
   } csl;
   bool in_flight = false;
   double t_solve_begin = 0;
@@ -484,17 +484,40 @@ void run_admm(b200qp_solver* sv, const KArgs& a, float* ms) {
   finish_admm(sv, ms);
 }
 
-// algorithmic HBM bytes of one solve (DESIGN.md "byte model"), from the kernel's own counters
-double algo_bytes(const Work* w, long long iters, long long cg, int check_every) {
+// Byte models of one solve, from the kernel's own iteration counters (DESIGN.md "byte models").
+//   survey : SURVEY.md 8(d), the figure roofline.achieved uses.  B(M) = 12 nnz + 4 (rows + 1) + 8 rows + 8 cols per
+//            product y = M x; per PCG iteration B(P) + B(A) + B(A') + 8 vectors x 8n; per ADMM iteration B(A') (right-hand
+//            side) + B(A) (z~) + the fused vector pass 8 (5n + 10m); per termination check B(P) + B(A').
+//   engine : what THIS kernel's storage moves -- tile blobs instead of CSR arrays for the tile kernel, its own vector
+//            passes (residual-correction R phase reads P as well; V phase = 7 reads + 5 writes).
+double spmv_bytes(double nnz, double rows, double cols) { return 12 * nnz + 4 * (rows + 1) + 8 * rows + 8 * cols; }
+double algo_bytes_survey(const Work* w, long long iters, long long cg, int check_every) {
+  const double n = w->n, m = w->m;
+  const double bP = spmv_bytes(w->P.nnz, n, n), bA = spmv_bytes(w->A.nnz, m, n), bAt = spmv_bytes(w->A.nnz, n, m);
+  const double per_cg = bP + bA + bAt + 8 * 8 * n;
+  const double per_admm = bAt + bA + 8 * (5 * n + 10 * m);
+  const double checks = check_every > 0 ? (double)(iters / check_every) : 0.0;
+  return (double)cg * per_cg + (double)iters * per_admm + checks * (bP + bAt);
+}
+double algo_bytes_engine(const Work* w, long long iters, long long cg, int check_every) {
   const double n = w->n, m = w->m, zP = w->P.nnz, zA = w->A.nnz;
+  const double checks = check_every > 0 ? (double)(iters / check_every) : 0.0;
+  if (w->csl.enabled && !w->dist.connected) {
+    const double tN = w->csl.bytesN, tM = w->csl.bytesM;
+    const double R = tN + 8 * (n + m) + 8 * 4 * n;            // gathers x, w2; reads q, Minv; writes r, u
+    const double B = tM + 8 * n + 8 * 2 * m;                  // gathers u; reads rho; writes t
+    const double C = tN + 8 * (n + m) + 8 * 2 * n;            // gathers u, t; reads u; writes w
+    const double V = 8 * 12 * n;                              // reads u, w, Minv, r, p, s, d; writes p, s, d, r, u
+    const double Z = tM + 8 * n + 8 * 11 * m + 8 * 3 * n;
+    return (double)iters * (R + Z) + (double)cg * (B + C + V) + checks * (2 * tN + 8 * 2 * m + 8 * 4 * n + 8 * 6 * m);
+  }
   const double spP = 12 * zP + 4 * (n + 1), spA = 12 * zA + 4 * (m + 1), spAt = 12 * zA + 4 * (n + 1);
   const double R = spP + spAt + 8 * n /*x*/ + 8 * m /*w2*/ + 8 * 2 * n /*q,Minv*/ + 8 * 2 * n /*r,p*/;
   const double C1 = spA + 8 * n + 8 * m + 8 * m;
   const double C2 = spP + spAt + 8 * n + 8 * m + 8 * n + 8 * n;
   const double C3 = 8 * n * 7, C4 = 8 * n * 4;
   const double Z = spA + 8 * n + 8 * m * 11 + 8 * n * 3;
-  const double chk = (check_every > 0) ? (double)(iters / check_every) * (12 * zA + 8 * m + 8 * 4 * n + 8 * 6 * m) : 0;
-  return (double)iters * (R + Z) + (double)cg * (C1 + C2 + C3 + C4) + chk;
+  return (double)iters * (R + Z) + (double)cg * (C1 + C2 + C3 + C4) + checks * (12 * zA + 8 * m + 8 * 4 * n + 8 * 6 * m);
 }
 
 }  // namespace
@@ -796,7 +819,7 @@ b200qp_int b200qp_setup(b200qp_solver** solverp, const b200qp_csc* P, const b200
           if (const char* e = std::getenv("B200QP_GRID")) wantG = std::atoll(e);
           cs.G = (int)std::min<long long>(std::max<long long>(wantG, 1), max_coop);
           cs.ntilesN = HN.ntiles; cs.ntilesM = HM.ntiles;
-          cs.tile_bytes = 16.0 * HN.toff[HN.ntiles] + 16.0 * HM.toff[HM.ntiles];
+          cs.bytesN = 16.0 * HN.toff[HN.ntiles]; cs.bytesM = 16.0 * HM.toff[HM.ntiles];
           std::vector<int> ptn, ptm;
           csl_partition(HN, cs.G, ptn);
           csl_partition(HM, cs.G, ptm);
@@ -913,7 +936,13 @@ static b200qp_int solve_end(b200qp_solver* solver) {
     w->stats.admm_iters = o.iter; w->stats.cg_iters = o.cg_iters; w->stats.grid_barriers = o.barriers;
     w->stats.kernel_ms = ms;
     for (int i = 0; i < 8; ++i) w->stats.phase_ms[i] = o.phase_ns[i] * 1e-6;
-    w->stats.algo_bytes = algo_bytes(w, o.iter, o.cg_iters, st->check_termination);
+    w->stats.algo_bytes = algo_bytes_survey(w, o.iter, o.cg_iters, st->check_termination);
+    w->stats.algo_bytes_engine = algo_bytes_engine(w, o.iter, o.cg_iters, st->check_termination);
+    w->stats.spmv_bytes[0] = spmv_bytes(w->A.nnz, w->m, w->n);
+    w->stats.spmv_bytes[1] = spmv_bytes(w->P.nnz, w->n, w->n) + spmv_bytes(w->A.nnz, w->n, w->m);
+    w->stats.kernel_kind = w->dist.connected ? 2 : (w->csl.enabled ? 1 : 0);
+    w->stats.ring_stages = w->csl.enabled ? w->csl.S : 0;
+    w->stats.ring_stage_bytes = w->csl.enabled ? w->csl.capb : 0;
     if (w->dist.connected) { w->stats.grid = w->dist.G; }
     info->solve_time = now_s() - t0;
 
@@ -1475,14 +1504,22 @@ struct b200qp_spmv_plan {
   int T = 0, grid_tile = 1;
   DBuf<double> x, y;
   DBuf<char> flush;
+  bool flush_init = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   int sms = 148;
+  // production tile scheme (variant 3)
+  bool csl_ok = false;
+  DBuf<unsigned> csl_toff;
+  DBuf<unsigned char> csl_blob;
+  DBuf<int> csl_part;
+  int csl_ntiles = 0, csl_S = 0, csl_capb = 0, csl_G = 1;
+  size_t csl_smem = 0;
 };
 
-b200qp_int b200qp_spmv_num_variants(void) { return 3; }
+b200qp_int b200qp_spmv_num_variants(void) { return 4; }
 const char* b200qp_spmv_variant_name(b200qp_int v) {
-  return v == 0 ? "group" : v == 1 ? "stream-tma" : v == 2 ? "scalar" : "?";
+  return v == 0 ? "group" : v == 1 ? "stream-tma" : v == 2 ? "scalar" : v == 3 ? "tile-tma" : "?";
 }
 
 b200qp_int b200qp_spmv_plan_create(b200qp_spmv_plan** planp, b200qp_int rows, b200qp_int cols, const b200qp_int* ptr,
@@ -1517,6 +1554,30 @@ b200qp_int b200qp_spmv_plan_create(b200qp_spmv_plan** planp, b200qp_int rows, b2
     pl->tiles.upload(tiles.data(), tiles.size(), pl->stream);
     pl->cta_tile.alloc(cta_tile.size());
     pl->cta_tile.upload(cta_tile.data(), cta_tile.size(), pl->stream);
+    {   // variant 3: the compacted-slice tiles of the persistent kernel (values packed on the host here)
+      CslHost H;
+      csl_build(rows, p.data(), i.data(), nullptr, nullptr, H);
+      const size_t budget = 100 * 1024;
+      const unsigned capb = ((H.max_tile_bytes + 127u) / 128u) * 128u;
+      const int S = capb ? (int)std::min<size_t>(32, budget / capb) : 0;
+      if (H.ok && S >= CSL_NWC + 2) {
+        double* bd = reinterpret_cast<double*>(H.blob.data());
+        for (size_t e = 0; e < H.src1.size(); ++e) bd[H.dst1[e]] = v[H.src1[e]];
+        const size_t smem = (size_t)S * capb;
+        const int occ2 = b200qp_spmv_csl_prepare(budget, smem);
+        if (occ2 >= 1) {
+          pl->csl_S = S; pl->csl_capb = (int)capb; pl->csl_smem = smem; pl->csl_ntiles = H.ntiles;
+          pl->csl_G = std::max(1, std::min(H.ntiles / 4 + 1, occ2 * pl->sms));
+          std::vector<int> pt;
+          csl_partition(H, pl->csl_G, pt);
+          pl->csl_toff.alloc(H.toff.size()); pl->csl_toff.upload(H.toff.data(), H.toff.size(), pl->stream);
+          pl->csl_blob.alloc(H.blob.size() + 16); pl->csl_blob.upload(H.blob.data(), H.blob.size(), pl->stream);
+          pl->csl_part.alloc(pt.size()); pl->csl_part.upload(pt.data(), pt.size(), pl->stream);
+          CK(cudaStreamSynchronize(pl->stream));
+          pl->csl_ok = true;
+        }
+      }
+    }
     CK(cudaStreamSynchronize(pl->stream));
   } catch (int code) {
     delete pl;
@@ -1530,7 +1591,11 @@ static void spmv_launch(b200qp_spmv_plan* pl, int variant) {
   const CsrMat M = pl->M.view();
   const int rows = M.rows;
   if (!rows) return;
-  if (variant == 1) {
+  if (variant == 3) {
+    if (!pl->csl_ok) throw (int)B200QP_FUNC_NOT_IMPLEMENTED;     // rows longer than 255 entries / a tile larger than a ring stage
+    const CslStream CS{M.rows, pl->csl_ntiles, pl->csl_toff.p, pl->csl_blob.p};
+    b200qp_spmv_csl_launch(CS, pl->csl_part.p, pl->csl_G, pl->csl_S, pl->csl_capb, pl->csl_smem, pl->x.p, pl->y.p, pl->stream);
+  } else if (variant == 1) {
     const TileMat TM{M.rows, M.cols, M.nnz, pl->T, M.ptr, M.idx, M.val, pl->tiles.p, nullptr};
     k_spmv_tile<<<pl->grid_tile, NT, TS_SMEM, pl->stream>>>(TM, pl->cta_tile.p, pl->x.p, pl->y.p);
   } else if (variant == 2) {
@@ -1556,8 +1621,14 @@ b200qp_int b200qp_spmv_plan_run(b200qp_spmv_plan* pl, const b200qp_float* x_host
     if (flush_l2 && !pl->flush.p) pl->flush.alloc(FL);
     double total = 0.0;
     reps = std::max(reps, 1);
+    if (flush_l2 && !pl->flush_init) { CK(cudaMemsetAsync(pl->flush.p, 0, FL, pl->stream)); pl->flush_init = true; }
     for (int r = 0; r < reps; ++r) {
-      if (flush_l2) CK(cudaMemsetAsync(pl->flush.p, r & 0xff, FL, pl->stream));
+      // flush by READING a buffer larger than L2 (a memset leaves 126 MB of dirty lines whose write-back competes with
+      // the timed launch), then bring x back: inside the solver the gathered vector was just written and is L2-resident
+      if (flush_l2) {
+        k_touch<<<pl->sms * 4, 512, 0, pl->stream>>>(reinterpret_cast<const double*>(pl->flush.p), (long long)(FL / 8), pl->y.p);
+        k_touch<<<pl->sms, 512, 0, pl->stream>>>(pl->x.p, (long long)pl->M.cols, pl->y.p);
+      }
       CK(cudaEventRecord(pl->e0, pl->stream));
       spmv_launch(pl, variant);
       CK(cudaEventRecord(pl->e1, pl->stream));
@@ -1579,6 +1650,7 @@ void b200qp_spmv_plan_destroy(b200qp_spmv_plan* pl) {
   if (!pl) return;
   cudaSetDevice(pl->device);
   pl->M.free(); pl->tiles.free(); pl->cta_tile.free(); pl->x.free(); pl->y.free(); pl->flush.free();
+  pl->csl_toff.free(); pl->csl_blob.free(); pl->csl_part.free();
   if (pl->e0) cudaEventDestroy(pl->e0);
   if (pl->e1) cudaEventDestroy(pl->e1);
   if (pl->stream) cudaStreamDestroy(pl->stream);

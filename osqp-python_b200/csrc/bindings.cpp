@@ -186,7 +186,10 @@ class Solver {
     for (int i = 0; i < 8; ++i) ph.append(st.phase_ms[i]);
     return py::dict("phase_ms"_a = ph, "admm_iters"_a = st.admm_iters, "cg_iters"_a = st.cg_iters, "grid_barriers"_a = st.grid_barriers,
                     "kernel_ms"_a = st.kernel_ms, "algo_bytes"_a = st.algo_bytes, "grid"_a = st.grid,
-                    "block"_a = st.block, "n"_a = st.n, "m"_a = st.m, "nnzP_full"_a = st.nnzP_full, "nnzA"_a = st.nnzA);
+                    "block"_a = st.block, "n"_a = st.n, "m"_a = st.m, "nnzP_full"_a = st.nnzP_full, "nnzA"_a = st.nnzA,
+                    "algo_bytes_engine"_a = st.algo_bytes_engine, "spmv_bytes_A"_a = st.spmv_bytes[0],
+                    "spmv_bytes_K"_a = st.spmv_bytes[1], "kernel_kind"_a = st.kernel_kind,
+                    "ring_stages"_a = st.ring_stages, "ring_stage_bytes"_a = st.ring_stage_bytes);
   }
 
  private:

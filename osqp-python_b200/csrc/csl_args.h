@@ -30,3 +30,7 @@ struct CArgs {                   // what the CSL kernel needs beyond KArgs
 
 // the kernel lives in its own translation unit (b200qp_csl.cu); the host driver launches it through this handle
 const void* b200qp_csl_kernel();
+// standalone tile SpMV (same translation unit): occupancy query (0 = cannot run) and launch
+int b200qp_spmv_csl_prepare(size_t budget, size_t smem);
+void b200qp_spmv_csl_launch(const b200qp::CslStream& M, const int* part, int G, int S, int capb, size_t smem, const double* x,
+                            double* y, cudaStream_t stream);

@@ -9,3 +9,7 @@ for p in (ROOT, os.path.join(ROOT, "osqp-python_b200"), os.path.join(ROOT, "test
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+# The reference's own test files (tests/ref/suite, and their assembled copy under tests/ref/_work) are run by
+# tests/test_refsuite.py in a subprocess with the reference facade on the path; they are not part of this collection.
+collect_ignore_glob = ["ref/suite/*", "ref/_work/*"]

@@ -19,7 +19,24 @@ def _mats():
     out["empty"] = sparse.csr_matrix((7, 5))
     out["dense_rows"] = sparse.random(64, 9000, density=0.6, random_state=rng, format="csr")
     out["wide"] = sparse.random(20000, 50, density=0.2, random_state=rng, format="csr")
+    # row lengths 0..200 in no order: exercises the ballot-compacted columns of the tile layout (lanes drop out one by one)
+    lens = rng.integers(0, 201, size=1000)
+    rows = np.repeat(np.arange(1000), lens)
+    cols = np.concatenate([rng.choice(7000, size=k, replace=False) for k in lens])
+    out["mixed_lengths"] = sparse.csr_matrix((rng.standard_normal(len(rows)), (rows, cols)), shape=(1000, 7000))
     return out
+
+
+def _tile_eligible(M):
+    """The tile layout stores row lengths in a byte and needs every 32-row tile to fit one ring stage (csl_host.h)."""
+    lens = np.diff(M.indptr)
+    if lens.size == 0:
+        return True
+    if lens.max() > 255:
+        return False
+    pad = (-len(lens)) % 32
+    per_tile = np.pad(lens, (0, pad)).reshape(-1, 32).sum(axis=1)
+    return 80 + 12 * (int(per_tile.max()) + 3) <= (100 * 1024) // 10
 
 
 @pytest.mark.parametrize("name", list(_mats().keys()))
@@ -30,7 +47,12 @@ def test_spmv_variants_match_scipy(name):
     x = np.random.default_rng(1).standard_normal(M.shape[1])
     want = M @ x
     scale = max(1.0, float(np.max(np.abs(want))) if want.size else 1.0)
+    assert "tile-tma" in lowlevel.variants()
     for v, vname in enumerate(lowlevel.variants()):
+        if vname == "tile-tma" and not _tile_eligible(M):
+            with pytest.raises(RuntimeError):          # refused loudly, never a silent fallback
+                lowlevel.spmv_host(M, x, variant=v)
+            continue
         got = lowlevel.spmv_host(M, x, variant=v)
         assert np.max(np.abs(got - want)) <= 1e-12 * scale, f"variant {vname} on {name}"
 
