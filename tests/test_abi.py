@@ -36,7 +36,7 @@ def test_default_settings_through_c_abi():
     assert s.linsys_solver == 2 and s.rho == 0.1 and s.sigma == 1e-6 and s.alpha == 1.6
     assert s.max_iter == 4000 and s.check_termination == 25 and s.cg_max_iter == 100 and s.cg_tol_fraction == 0.1
     assert lowlevel.lib().b200qp_capabilities() == 0x02 | 0x08 | 0x10
-    assert lowlevel.variants() == ["group", "stream-tma", "scalar"]
+    assert lowlevel.variants() == ["group", "stream-tma", "scalar", "tile-tma"]
 
 
 def test_extension_surface_matches_reference_facade():
