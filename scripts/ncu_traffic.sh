@@ -10,7 +10,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:admm
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-spmv --no-batch --no-structured > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 ncu -i gpurun_out/prof_admm_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_admm_${TAG}_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_admm_$TAG.ncu-rep --page details > gpurun_out/prof_admm_${TAG}_details.txt 2>/dev/null
-ncu -i gpurun_out/prof_admm_$TAG.ncu-rep --page source --csv --print-source cuda > gpurun_out/prof_admm_${TAG}_source.csv 2>/dev/null
+ncu -i gpurun_out/prof_admm_$TAG.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/prof_admm_${TAG}_source.csv 2>/dev/null
 python - <<PY
 import csv, json
 rows = list(csv.reader(open("gpurun_out/prof_admm_${TAG}_raw.csv")))
