@@ -68,10 +68,9 @@ __device__ __forceinline__ TileView tile_view(const unsigned char* tp, int lane)
 // (ballot-compaction; none needed when every row of the tile has maxlen entries), all index loads, all gathers, all
 // value loads, then the FMAs in DESCENDING order -- the first FMA needs the last gather, which keeps ptxas from
 // sinking every load next to its use.  (Ten at a time was measured: same rate, 1 KB of spills at 128 registers.)
-template <int NV, bool SMEM>
+template <int NV, bool SMEM, int U = 5>
 __device__ __forceinline__ void part_dot(const int* ip, const double* vp, int len, int maxlen, const double* __restrict__ va,
                                          const double* __restrict__ vb, double& sa, double& sb, int j_begin = 0, int pos0 = 0) {
-  constexpr int U = 5;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const bool uniform = __all_sync(0xffffffffu, len == maxlen);

@@ -797,7 +797,12 @@ b200qp_int b200qp_setup(b200qp_solver** solverp, const b200qp_csc* P, const b200
         csl_build(n, Pp.data(), Pj.data(), Atp.data(), Ati.data(), HN);
         csl_build(m, Ap.data(), Aj.data(), nullptr, nullptr, HM);
       }
-      const size_t ring_budget = 100 * 1024;       // per CTA, two CTAs per SM
+      // per CTA, two CTAs per SM.  The unified L1 / shared-memory array is carved in steps (.., 164, 196, 228 KB): two CTAs
+      // whose dynamic + static + 1 KB reserved shared memory exceed 196 KB push the carve-out to 228 KB and leave 28 KB of
+      // L1, which is also where the sectors of the in-flight gathers wait -- measured: A u 47 us with a 196 KB carve-out,
+      // 71 us with 228 KB (profiles/r2b_agather_lab_smem_carveout_sweep.log).  94 KB + 2.6 KB static + 1 KB <= 98 KB.
+      size_t ring_budget = CSL_RING_BUDGET;
+      if (const char* e = std::getenv("B200QP_RING_KB")) ring_budget = (size_t)std::max(16, std::min(110, std::atoi(e))) * 1024;
       const unsigned capb = ((std::max(HN.max_tile_bytes, HM.max_tile_bytes) + 127u) / 128u) * 128u;
       const int S = capb ? (int)std::min<size_t>(32, ring_budget / capb) : 0;
       if (want && HN.ok && HM.ok && S >= CSL_NWC + 2) {
@@ -810,7 +815,7 @@ b200qp_int b200qp_setup(b200qp_solver** solverp, const b200qp_csc* P, const b200
         const void* fn = b200qp_csl_kernel();
         // a per-function attribute shared by every solver of the process: always the full budget (a per-solver value
         // would race between solvers that are set up from different threads)
-        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_budget));
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ring_budget, CSL_RING_BUDGET)));
         int occ2 = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fn, CSL_NT, cs.smem));
         if (occ2 >= 1) {
@@ -1557,7 +1562,7 @@ b200qp_int b200qp_spmv_plan_create(b200qp_spmv_plan** planp, b200qp_int rows, b2
     {   // variant 3: the compacted-slice tiles of the persistent kernel (values packed on the host here)
       CslHost H;
       csl_build(rows, p.data(), i.data(), nullptr, nullptr, H);
-      const size_t budget = 100 * 1024;
+      const size_t budget = CSL_RING_BUDGET;     // see b200qp_setup: stay inside the 196 KB shared-memory carve-out
       const unsigned capb = ((H.max_tile_bytes + 127u) / 128u) * 128u;
       const int S = capb ? (int)std::min<size_t>(32, budget / capb) : 0;
       if (H.ok && S >= CSL_NWC + 2) {

@@ -10,6 +10,7 @@ constexpr int CSL_NT = CSL_NWC * 32 + 32;  // + one producer warp
 constexpr int CSL_NW = CSL_NT / 32;
 constexpr int CSL_CT = CSL_NWC * 32;       // consumer threads
 constexpr int CSL_HDR = 80;                // header + two length arrays
+constexpr size_t CSL_RING_BUDGET = 94 * 1024;   // dynamic shared memory per CTA (two CTAs per SM inside a 196 KB carve-out)
 
 struct CslStream {
   int rows, ntiles;
