@@ -181,8 +181,11 @@ typedef struct {
                              CSR kernel R, C1 (A p), C2 (K p), C3, C4, Z; tile kernel R, B (A u), C (K u), V, -, Z */
   double algo_bytes_engine; /* same launch, counted with the engine's own storage (tile blobs, its vector passes) */
   double spmv_bytes[2];   /* algorithmic bytes of ONE A-product phase / ONE K-product phase (SURVEY 8d model)  */
-  b200qp_int kernel_kind; /* 0 = CSR lanes-per-row kernel, 1 = compacted-slice tiles + TMA ring, 2 = multi-GPU */
+  b200qp_int kernel_kind; /* 0 = CSR lanes-per-row kernel, 1 = compacted-slice tiles + TMA ring, 2 = multi-GPU (CSR),
+                             3 = multi-GPU (tiles + TMA ring, flat NVLink barrier)                                 */
   b200qp_int ring_stages, ring_stage_bytes;
+  double autotune_ms[2];  /* setup-time measurement behind the ring depth: 3 ADMM iterations with the 94 KB ring
+                             (196 KB shared-memory carve-out) / the 108 KB ring (228 KB); 0 = not measured          */
 } b200qp_stats;
 
 /* ---- the reference path ------------------------------------------------------------------ */

@@ -118,8 +118,10 @@ class DistSolver:
         if rc:
             raise RuntimeError(f"multi-GPU solve failed with code {rc} on rank {self.rank}")
         y, pc = self.solver.solution.y, self.solver.solution.prim_inf_cert
-        if gather_y and self.world > 1:
-            lo, hi = self.solver.dist_row_range()
+        lo, hi = self.solver.dist_row_range()
+        # tile kernel: the last check iteration pushed y and the certificate to every rank over NVLink -- the row range is
+        # [0, m) and there is nothing to gather; the CSR fallback kernel keeps slabs and needs the host-side all-gather
+        if gather_y and self.world > 1 and (lo, hi) != (0, self.m):
             y, pc = gather_slabs(np.stack([y, pc]), lo, hi, self.m, self.world, self._dist, self._torch, self._dev)
         return _result(self.solver, y, pc)
 

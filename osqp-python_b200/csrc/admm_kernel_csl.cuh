@@ -24,6 +24,7 @@
 //   B  m-tiles: t = rho .* (A u)         C  n-tiles: w = P u + sigma u + A' t, <w,u>
 //   V  n-elements: p, s, d, r, u = M^-1 r, <r,u>, |r|inf       (128-bit loads / stores)
 #pragma once
+#include <cstdio>
 #include <type_traits>
 
 #include "admm_kernel.cuh"
@@ -195,7 +196,52 @@ __device__ __forceinline__ void grid_reduce_load_w(const double* bank, int G, un
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c) {
+// After the barrier: every CTA folds all Gt partials of every slot with ALL its threads (thread t takes t, t + NT, ...;
+// warp butterfly; warps in order) -- one L2 round trip per slot whatever Gt is (8 GPUs: 2368 partials), fixed order.
+template <int K, int NWARPS>
+__device__ __forceinline__ void grid_reduce_load_all(const double* bank, int Gt, unsigned maxmask, double* s_tot, double* s_red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const bool mx = (maxmask >> k) & 1u;
+    acc[k] = mx ? __longlong_as_double(0xfff0000000000000LL) : 0.0;
+    for (int cc = threadIdx.x; cc < Gt; cc += NWARPS * 32) acc[k] = combine(acc[k], __ldcg(bank + (size_t)k * Gt + cc), mx);
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double r = warp_combine(acc[k], (maxmask >> k) & 1u);
+    if (lane == 0) s_red[k * NWARPS + warp] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    const bool mx = (maxmask >> threadIdx.x) & 1u;
+    double t = s_red[threadIdx.x * NWARPS];
+    for (int w = 1; w < NWARPS; ++w) t = combine(t, s_red[threadIdx.x * NWARPS + w], mx);
+    s_tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+}
+
+// system-scope operations of the multi-GPU instantiation (peer-mapped memory over NVLink / NVSwitch)
+__device__ __forceinline__ void csl_st_sys(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void csl_st_sys2(double2* p, double2 v) {
+  asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void csl_red_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long csl_ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <bool DIST>
+__global__ void __launch_bounds__(CSL_NT, 2)
+admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c, const __grid_constant__ XCsl x) {
   extern __shared__ __align__(128) unsigned char ring[];   // [S][capb]
   __shared__ double s_red[KMAX * CSL_NW];
   __shared__ double s_tot[KMAX];
@@ -211,6 +257,11 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
   const int tm0 = c.part_tm[cta], tm1 = c.part_tm[cta + 1], TM = tm1 - tm0;
   const int n0 = min(tn0 * 32, a.n), n1 = min(tn1 * 32, a.n);
   const int m0 = min(tm0 * 32, a.m), m1 = min(tm1 * 32, a.m);
+  // multi-GPU: the tile ranges cover this rank's slab / slice only; x is replicated (every rank updates all of it) and
+  // every rank re-derives the whole rho vector, over uniform shares
+  const int un0 = DIST ? x.part_un[cta] : n0, un1 = DIST ? x.part_un[cta + 1] : n1;
+  const int um0 = DIST ? x.part_um[cta] : m0, um1 = DIST ? x.part_um[cta + 1] : m1;
+  const int Gt = DIST ? x.Gtot : G;          // partials per reduction slot
   GridSync sync{a.ctrl, G, 0ULL, &s_ok};
   const double NEG_INF = __longlong_as_double(0xfff0000000000000LL);
 
@@ -245,7 +296,88 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
   double rz = 0, r0max = 0;
   bool time_up = false, tl_pending = false;
 
-  auto bank = [&]() -> double* { return a.red + (size_t)(sync.epoch & 1ULL) * KMAX * G; };
+  // ---- how the CTAs of the job meet: grid barrier (one GPU) or flat cross-GPU barrier; partial banks; pushes
+  const size_t xbank_par = DIST ? (size_t)KMAX * (size_t)x.Gtot : 0;
+  auto barrier = [&]() -> bool {
+    if constexpr (!DIST) {
+      return sync.barrier();
+    } else {
+      __syncthreads();                       // every thread's stores of this phase (pushes included) are issued
+      sync.epoch++;
+      if (tid < CSL_MAXW && tid < x.world) {
+        unsigned long long* dst = x.arrive[0];
+#pragma unroll
+        for (int h = 1; h < CSL_MAXW; ++h) if (tid == h) dst = x.arrive[h];
+        __threadfence_system();              // cumulative: orders the CTA's earlier peer stores before the arrival
+        csl_red_release_sys(dst, 1ULL);
+      }
+      if (tid == 0) {
+        const unsigned long long* mine = x.arrive[0];
+#pragma unroll
+        for (int h = 1; h < CSL_MAXW; ++h) if (x.rank == h) mine = x.arrive[h];
+        const unsigned long long target = (x.epoch0 + sync.epoch) * (unsigned long long)x.Gtot;
+        int ok = 1;
+        unsigned spins = 0;
+        unsigned long long t0 = 0;
+        while (csl_ld_acquire_sys(mine) < target) {
+          if ((++spins & 0x3ffu) == 0) {
+            if (*(volatile int*)&a.ctrl->abort) { ok = 0; break; }
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 10000000000ULL) { ok = 0; break; }   // 10 s watchdog
+          }
+        }
+        if (*(volatile int*)&a.ctrl->abort) ok = 0;
+        if (!ok) {     // tell everybody, so that no rank spins until its own watchdog
+#pragma unroll
+          for (int h = 0; h < CSL_MAXW; ++h) if (h < x.world) *(volatile int*)x.abort_flag[h] = 1;
+        }
+        s_ok = ok;
+      }
+      __syncthreads();
+      return s_ok != 0;
+    }
+  };
+  // CTA partials of K slots -> the bank every CTA will fold after the next barrier (on every rank when DIST)
+  auto reduce_store = [&](auto& v, auto k_tag, unsigned maxmask) {
+    constexpr int K = decltype(k_tag)::value;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double r = warp_combine(v[k], (maxmask >> k) & 1u);
+      if (lane == 0) s_red[k * CSL_NW + warp] = r;
+    }
+    __syncthreads();
+    if (tid < K) {
+      const bool mx = (maxmask >> tid) & 1u;
+      double acc = s_red[tid * CSL_NW];
+      for (int w = 1; w < CSL_NW; ++w) acc = combine(acc, s_red[tid * CSL_NW + w], mx);
+      if constexpr (DIST) {
+        const size_t off = (size_t)(sync.epoch & 1ULL) * xbank_par + (size_t)tid * x.Gtot + x.goff + cta;
+#pragma unroll
+        for (int h = 0; h < CSL_MAXW; ++h) if (h < x.world) csl_st_sys(x.xbank[h] + off, acc);
+      } else {
+        a.red[(size_t)(sync.epoch & 1ULL) * KMAX * G + tid * G + cta] = acc;
+      }
+    }
+  };
+  // fold after the barrier (the bank index is the parity the partials were stored under: epoch has advanced by one)
+  auto reduce_load = [&](auto k_tag, unsigned maxmask) {
+    constexpr int K = decltype(k_tag)::value;
+    const unsigned long long par = (sync.epoch - 1ULL) & 1ULL;
+    const double* bk;
+    if constexpr (DIST) {
+      const double* mine = x.xbank[0];
+#pragma unroll
+      for (int h = 1; h < CSL_MAXW; ++h) if (x.rank == h) mine = x.xbank[h];
+      bk = mine + (size_t)par * xbank_par;
+    } else {
+      bk = a.red + (size_t)par * KMAX * G;
+    }
+    grid_reduce_load_all<K, CSL_NW>(bk, Gt, maxmask, s_tot, s_red);
+  };
+  // all-gather by stores: the producing thread writes its element into every peer's copy
+#define CSL_PUSH(tab, i, v) do { if constexpr (DIST) { _Pragma("unroll") for (int h_ = 0; h_ < CSL_MAXW; ++h_) if (h_ < x.world && h_ != x.rank) csl_st_sys(x.tab[h_] + (i), (v)); } } while (0)
+#define CSL_PUSH2(tab, i2, v) do { if constexpr (DIST) { _Pragma("unroll") for (int h_ = 0; h_ < CSL_MAXW; ++h_) if (h_ < x.world && h_ != x.rank) csl_st_sys2(reinterpret_cast<double2*>(x.tab[h_]) + (i2), (v)); } } while (0)
 
   // ---- ring state -----------------------------------------------------------------------------------------------
   // ring_q = tiles issued / consumed so far, modulo 2S (stage = q % S, parity = q >= S); identical in every thread.
@@ -267,14 +399,20 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
       const int nt = min(31, i1 - ib);
       for (int i = 0; i < nt; ++i) {
         const unsigned o0 = __shfl_sync(0xffffffffu, mine, i), o1 = __shfl_sync(0xffffffffu, mine, i + 1);
+        int alive = 1;
         if (lane == 0) {
           const int stg = q >= S ? q - S : q;
           const unsigned par = q >= S ? 1u : 0u;
-          mbar_wait(&bar_empty[stg], par);          // previous occupant released (or the initial arrival)
-          const uint32_t bytes = (o1 - o0) * 16u;
-          mbar_expect_tx(&bar_full[stg], bytes);
-          bulk_g2s_hint(ring + (size_t)stg * c.capb, st.blob + (size_t)o0 * 16u, bytes, &bar_full[stg], pol);
+          if (!mbar_wait_guard(&bar_empty[stg], par, &a.ctrl->abort)) {   // previous occupant released (or the initial arrival)
+            if (c.debug) printf("[b200qp csl] producer timeout: cta %d stage %d q %d tile %d of [%d,%d) q0 %d S %d epoch %llu\n", cta, stg, q, ib + i, i0, i1, q0, S, sync.epoch);
+            alive = 0;
+          } else {
+            const uint32_t bytes = (o1 - o0) * 16u;
+            mbar_expect_tx(&bar_full[stg], bytes);
+            bulk_g2s_hint(ring + (size_t)stg * c.capb, st.blob + (size_t)o0 * 16u, bytes, &bar_full[stg], pol);
+          }
         }
+        if (!__shfl_sync(0xffffffffu, alive, 0)) return;     // the abort flag is up: the next barrier ends the kernel
         q = q + 1 == 2 * S ? 0 : q + 1;
         __syncwarp();
       }
@@ -303,7 +441,10 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
       int q = q_add(q0, warp);
       for (int i = warp; i < T; i += CSL_NWC) {
         const int stg = q >= S ? q - S : q;
-        mbar_wait(&bar_full[stg], q >= S ? 1u : 0u);
+        if (!__all_sync(0xffffffffu, mbar_wait_guard(&bar_full[stg], q >= S ? 1u : 0u, &a.ctrl->abort))) {
+          if (c.debug && lane == 0) printf("[b200qp csl] consumer timeout: cta %d warp %d stage %d q %d tile %d of %d q0 %d S %d epoch %llu pre %d\n", cta, warp, stg, q, i, T, q0, S, sync.epoch, pre_issued);
+          break;
+        }
         const TileView tv = tile_view<true>(ring + (size_t)stg * c.capb, lane);
         body(t0 + i, tv, [&] { __syncwarp(); if (lane == 0) csl_mbar_arrive(&bar_empty[stg]); }, std::true_type{});
         q = q_add(q, CSL_NWC);
@@ -317,11 +458,11 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
     if (producer && lane == 0)
       for (int i = 0; i < pre_issued; ++i) {
         const int q = q_add(ring_q, i);
-        mbar_wait(&bar_full[q >= S ? q - S : q], q >= S ? 1u : 0u);
+        if (!mbar_wait_guard(&bar_full[q >= S ? q - S : q], q >= S ? 1u : 0u, &a.ctrl->abort)) break;
       }
   };
 #define CSL_DIE() do { if (cta == 0 && tid == 0) a.out->aborted = 1; return; } while (0)
-#define CSL_BARRIER_OR_DIE() do { if (!sync.barrier()) CSL_DIE(); } while (0)
+#define CSL_BARRIER_OR_DIE() do { if (!barrier()) CSL_DIE(); } while (0)
 
   __shared__ long long t_phase[8];
   __shared__ unsigned long long t_mark;
@@ -339,7 +480,9 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
     const int row = tile * 32 + lane;
     if (row < a.m) {
       a.ax[row] = acc;
-      a.w2[row] = a.rho_v[row] * (a.z[row] - acc) - a.y[row];
+      const double w2n = a.rho_v[row] * (a.z[row] - acc) - a.y[row];
+      a.w2[row] = w2n;
+      CSL_PUSH(w2, row, w2n);
     }
   });
   CSL_BARRIER_OR_DIE();
@@ -354,6 +497,7 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
     const double uj = a.Minv[row] * rj;
     a.r[row] = rj;
     a.p[row] = uj;
+    CSL_PUSH(p, row, uj);
     v[R_RZ] += rj * uj;
     v[R_R0] = nanmax(v[R_R0], fabs(rj));
     if constexpr (FULL) {
@@ -375,15 +519,15 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
   };
   constexpr int H_TL = 2, H_K = 3;
   constexpr unsigned H_MAXMASK = (1u << R_R0) | (1u << H_TL);
-  auto load_R = [&](const double* bk, bool full) {
+  auto load_R = [&](bool full) {
     if (!full) {
-      grid_reduce_load_w<H_K, CSL_NW>(bk, G, H_MAXMASK, s_tot);
+      reduce_load(std::integral_constant<int, H_K>{}, H_MAXMASK);
       rz = s_tot[R_RZ];
       r0max = s_tot[R_R0];
       time_up = s_tot[H_TL] > 0.5;
       return;
     }
-    grid_reduce_load_w<R_K, CSL_NW>(bk, G, R_MAXMASK, s_tot);
+    reduce_load(std::integral_constant<int, (int)R_K>{}, R_MAXMASK);
     rz = s_tot[R_RZ];
     r0max = s_tot[R_R0];
     time_up = s_tot[R_TL] > 0.5;
@@ -399,7 +543,7 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
     prim_res = t_prim;
     nprim = fmax(t_ax, t_z);
   };
-  auto phase_R = [&](auto full_tag) -> const double* {
+  auto phase_R = [&](auto full_tag) {
     constexpr bool FULL = decltype(full_tag)::value;
     constexpr int K = FULL ? (int)R_K : H_K;
     constexpr int TL = FULL ? (int)R_TL : H_TL;
@@ -428,6 +572,7 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
           const double uj = mi * rj;
           a.r[row] = rj;
           a.p[row] = uj;
+          CSL_PUSH(p, row, uj);
           v[R_RZ] += rj * uj;
           v[R_R0] = nanmax(v[R_R0], fabs(rj));
         }
@@ -435,12 +580,10 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
     });
     // the clock is sampled every iteration (upstream osqp_solve does; a check_termination = 0 solve must still stop)
     if (tid == 0) v[TL] = ((double)(global_timer_ns() - t_start) > a.time_limit_ns) ? 1.0 : 0.0;
-    double* bk = bank();
-    block_reduce_store_w<K, CSL_NW>(v, FULL ? R_MAXMASK : H_MAXMASK, bk, G, s_red);
-    return bk;
+    reduce_store(v, std::integral_constant<int, K>{}, FULL ? R_MAXMASK : H_MAXMASK);
   };
   // after a rho update: px is stored, only A'w2 (and the Jacobi diagonal) change.  Off the alternating ring: plain loads.
-  auto phase_R_lite = [&]() -> const double* {
+  auto phase_R_lite = [&]() {
     double v[H_K];
 #pragma unroll
     for (int i = 0; i < H_K; ++i) v[i] = 0.0;
@@ -457,9 +600,7 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
       }
     }
     if (tid == 0) v[H_TL] = ((double)(global_timer_ns() - t_start) > a.time_limit_ns) ? 1.0 : 0.0;
-    double* bk = bank();
-    block_reduce_store_w<H_K, CSL_NW>(v, H_MAXMASK, bk, G, s_red);
-    return bk;
+    reduce_store(v, std::integral_constant<int, H_K>{}, H_MAXMASK);
   };
 
   // n-rows SpMV + inf-norm for the infeasibility certificates (rare; plain loads): part 1 = P, part 2 = A'
@@ -474,11 +615,10 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
       const int row = tile * 32 + lane;
       if (row < a.n) v[0] = nanmax(v[0], fabs((Dinv_t ? Dinv_t[row] : 1.0) * scale * acc));
     }
-    double* bk = bank();
-    block_reduce_store_w<1, CSL_NW>(v, 1u, bk, G, s_red);
-    ok = sync.barrier();
+    reduce_store(v, std::integral_constant<int, 1>{}, 1u);
+    ok = barrier();
     if (!ok) return 0.0;
-    grid_reduce_load_w<1, CSL_NW>(bk, G, 1u, s_tot);
+    reduce_load(std::integral_constant<int, 1>{}, 1u);
     return s_tot[0];
   };
 
@@ -520,13 +660,13 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
     const bool full = chk || adp;
 
     {
-      const double* bk = full ? phase_R(std::true_type{}) : phase_R(std::false_type{});
+      if (full) phase_R(std::true_type{}); else phase_R(std::false_type{});
       CSL_BARRIER_OR_DIE();
-      load_R(bk, full);
+      load_R(full);
       mark(0);
     }
     if (time_up) tl_pending = true;
-    if (full && a.verbose && cta == 0 && tid == 0 && chk && !tlp) {
+    if (full && a.verbose && cta == 0 && tid == 0 && chk && !tlp && (!DIST || x.rank == 0)) {
       const int row = (k / (a.check_term > 0 ? a.check_term : 1)) - 1;
       if (row >= 0 && row < a.log_cap) {
         a.log[row] = LogRow{k, 0, obj, prim_res, dual_res, rho, (double)(global_timer_ns() - t_start) * 1e-6};
@@ -555,16 +695,32 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
       if (rho_new > a.adapt_tol * rho || rho_new < rho / a.adapt_tol) {
         rho = rho_new;
         rho_updates++;
-        for (int i = m0 + tid; i < m1; i += CSL_NT) {
-          const double rv = rho_of_type(a.ctype[i], rho, a.rho_is_vec, a.rho_eq_factor);
-          a.rho_v[i] = rv;
-          a.rho_inv[i] = 1.0 / rv;
-          a.w2[i] = rv * (a.z[i] - a.ax[i]) - a.y[i];
+        if constexpr (DIST) {
+          // every rank re-derives the whole rho vector (the A' rows of its slice gather all of it) ...
+          for (int i = um0 + tid; i < um1; i += CSL_NT) {
+            const double rv = rho_of_type(a.ctype[i], rho, a.rho_is_vec, a.rho_eq_factor);
+            a.rho_v[i] = rv;
+            a.rho_inv[i] = 1.0 / rv;
+          }
+          // ... and refreshes w2 on its own rows for everybody
+          for (int i = m0 + tid; i < m1; i += CSL_NT) {
+            const double rv = rho_of_type(a.ctype[i], rho, a.rho_is_vec, a.rho_eq_factor);
+            const double w2n = rv * (a.z[i] - a.ax[i]) - a.y[i];
+            a.w2[i] = w2n;
+            CSL_PUSH(w2, i, w2n);
+          }
+        } else {
+          for (int i = m0 + tid; i < m1; i += CSL_NT) {
+            const double rv = rho_of_type(a.ctype[i], rho, a.rho_is_vec, a.rho_eq_factor);
+            a.rho_v[i] = rv;
+            a.rho_inv[i] = 1.0 / rv;
+            a.w2[i] = rv * (a.z[i] - a.ax[i]) - a.y[i];
+          }
         }
         CSL_BARRIER_OR_DIE();
-        const double* bk = phase_R_lite();
+        phase_R_lite();
         CSL_BARRIER_OR_DIE();
-        load_R(bk, false);
+        load_R(false);
       }
     }
 
@@ -584,7 +740,7 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
           double acc, dummy;
           part_dot<1, SM>(tv.i1, tv.v1, tv.len1, tv.max1, a.p, nullptr, acc, dummy);
           done();
-          if (row < a.m) a.w[row] = rv * acc;
+          if (row < a.m) { const double tv_ = rv * acc; a.w[row] = tv_; CSL_PUSH(w, row, tv_); }
         });
         if (c.cta_ns) { __syncthreads(); if (tid == 0) c.cta_ns[2 * cta] += (long long)(global_timer_ns() - tb0); }
         CSL_BARRIER_OR_DIE();
@@ -606,11 +762,10 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
             v1[0] += uj * wj;
           }
         });
-        double* bk = bank();
-        block_reduce_store_w<1, CSL_NW>(v1, 0u, bk, G, s_red);
+        reduce_store(v1, std::integral_constant<int, 1>{}, 0u);
         if (c.cta_ns && tid == 0) c.cta_ns[2 * cta + 1] += (long long)(global_timer_ns() - tc0);
         CSL_BARRIER_OR_DIE();
-        grid_reduce_load_w<1, CSL_NW>(bk, G, 0u, s_tot);
+        reduce_load(std::integral_constant<int, 1>{}, 0u);
         mark(2);
         const double delta = s_tot[0];
         const double bj = (j == 0) ? 0.0 : gam / gam_prev;
@@ -648,6 +803,7 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
             upd(ui.x, wi.x, po.x, so.x, dold.x, ro.x, mi.x, pn.x, sn.x, dn.x, rn.x, un.x);
             upd(ui.y, wi.y, po.y, so.y, dold.y, ro.y, mi.y, pn.y, sn.y, dn.y, rn.y, un.y);
             p2[i] = pn; s2[i] = sn; d2[i] = dn; r2[i] = rn; uo2[i] = un;
+            CSL_PUSH2(p, (n0 >> 1) + i, un);
           }
           if (((n1 - n0) & 1) && tid == 0) {
             const int i = n1 - 1;
@@ -655,13 +811,13 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
             upd(__ldcg(a.p + i), __ldcg(a.kp + i), j > 0 ? c.ps[i] : 0.0, j > 0 ? c.ss[i] : 0.0, j > 0 ? a.d[i] : 0.0, a.r[i],
                 a.Minv[i], pn, sn, dn, rn, un);
             c.ps[i] = pn; c.ss[i] = sn; a.d[i] = dn; a.r[i] = rn; a.p[i] = un;
+            CSL_PUSH(p, i, un);
           }
         }
         have_d = true;
-        bk = bank();
-        block_reduce_store_w<2, CSL_NW>(v2, 2u, bk, G, s_red);
+        reduce_store(v2, std::integral_constant<int, 2>{}, 2u);
         CSL_BARRIER_OR_DIE();
-        grid_reduce_load_w<2, CSL_NW>(bk, G, 2u, s_tot);
+        reduce_load(std::integral_constant<int, 2>{}, 2u);
         mark(3);
         gam_prev = gam;
         gam = s_tot[0];
@@ -670,7 +826,19 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
       }
       if (status) break;
     }
-    if (!have_d) {
+    if constexpr (DIST) {
+      // the Z phase gathers from the whole step: all-gather d (every rank produced its slice), or zero every copy
+      if (have_d) {
+        const int npair = (n1 - n0) >> 1;
+        const double2* d2 = reinterpret_cast<const double2*>(a.d + n0);
+        for (int i = tid; i < npair; i += CSL_NT) { const double2 v = d2[i]; CSL_PUSH2(d, (n0 >> 1) + i, v); }
+        if (((n1 - n0) & 1) && tid == 0) { const double v = a.d[n1 - 1]; CSL_PUSH(d, n1 - 1, v); }
+      } else {
+        for (int i = un0 + tid; i < un1; i += CSL_NT) a.d[i] = 0.0;
+      }
+      CSL_BARRIER_OR_DIE();
+      mark(6);
+    } else if (!have_d) {
       for (int i = n0 + tid; i < n1; i += CSL_NT) a.d[i] = 0.0;
       CSL_BARRIER_OR_DIE();
     }
@@ -696,8 +864,11 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
         const double yn = y_old + dy;
         const double axn = fma(alpha, ad, ax_old);
         a.z[row] = zn; a.y[row] = yn; a.ax[row] = axn;
-        a.w2[row] = rv * (zn - axn) - yn;
+        const double w2n = rv * (zn - axn) - yn;
+        a.w2[row] = w2n;
+        CSL_PUSH(w2, row, w2n);
         if constexpr (FULL) {
+          CSL_PUSH(y, row, yn);
           const double ei = Einv_t ? Einv_t[row] : 1.0;
           const double pr = axn - zn;
           v[Z_SPRIM] = nanmax(v[Z_SPRIM], fabs(pr));
@@ -713,6 +884,7 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
           else if (!ufin) dyp = fmin(dy, 0.0);
           else if (!lfin) dyp = fmax(dy, 0.0);
           a.w[row] = dyp;
+          CSL_PUSH(w, row, dyp);
           v[Z_NDY] = nanmax(v[Z_NDY], fabs((E_t ? E_t[row] : 1.0) * dyp));
           v[Z_LHS] += (ufin ? ui * fmax(dyp, 0.0) : 0.0) + (lfin ? li * fmin(dyp, 0.0) : 0.0);
           // dual infeasibility rows (reference _osqp.py:861-872)
@@ -730,19 +902,18 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
         const int row = tile * 32 + lane;
         if (row < a.m) z_row(row, ad);
       });
-      for (int i = n0 + tid; i < n1; i += CSL_NT) a.x[i] = fma(alpha, __ldcg(a.d + i), a.x[i]);  // _osqp.py:664-668
+      for (int i = un0 + tid; i < un1; i += CSL_NT) a.x[i] = fma(alpha, __ldcg(a.d + i), a.x[i]);  // _osqp.py:664-668
       if constexpr (FULL) {
-        double* bk = bank();
-        block_reduce_store_w<Z_K, CSL_NW>(v, Z_MAXMASK, bk, G, s_red);
-        if (!sync.barrier()) return false;
-        grid_reduce_load_w<Z_K, CSL_NW>(bk, G, Z_MAXMASK, s_tot);
+        reduce_store(v, std::integral_constant<int, (int)Z_K>{}, Z_MAXMASK);
+        if (!barrier()) return false;
+        reduce_load(std::integral_constant<int, (int)Z_K>{}, Z_MAXMASK);
         s_prim = s_tot[Z_SPRIM];
         s_nprim = fmax(s_tot[Z_SAX], s_tot[Z_SZ]);
         t_prim = s_tot[Z_TPRIM]; t_ax = s_tot[Z_TAX]; t_z = s_tot[Z_TZ];
         ndy = s_tot[Z_NDY]; lhs = s_tot[Z_LHS]; vu = s_tot[Z_VU]; vl = s_tot[Z_VL]; sup = s_tot[Z_SUP];
         return true;
       } else {
-        return sync.barrier();
+        return barrier();
       }
     };
     if (!(full_n ? phase_Z(std::true_type{}) : phase_Z(std::false_type{}))) CSL_DIE();
@@ -756,6 +927,7 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
     for (int i = 0; i < 8; ++i) o->phase_ns[i] = t_phase[i];
     o->status = status; o->iter = k; o->rho_updates = rho_updates;
     o->cg_iters = cg_total; o->barriers = (long long)sync.epoch;
+    if constexpr (DIST) o->xepoch = (long long)(x.epoch0 + sync.epoch);
     o->obj = obj; o->dual_obj = dobj; o->gap = gap; o->prim_res = prim_res; o->dual_res = dual_res;
     o->rho = rho;
     const double pr = s_prim / (s_nprim + 1e-10), du = s_dual / (s_ndual + 1e-10);
@@ -764,6 +936,8 @@ __global__ void __launch_bounds__(CSL_NT, 2) admm_kernel_csl(const __grid_consta
   }
 #undef CSL_DIE
 #undef CSL_BARRIER_OR_DIE
+#undef CSL_PUSH
+#undef CSL_PUSH2
 }
 
 }  // namespace b200qp

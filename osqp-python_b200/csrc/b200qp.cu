@@ -167,6 +167,10 @@ struct Work {
     int G = 1, lgn = 8, lgm = 8;
     unsigned long long xepoch = 0;
     bool broken = false;
+    // tile kernel over several GPUs (admm_kernel_csl<true>): flat barrier, banks sized by the CTAs of all ranks
+    bool use_csl = false;
+    int goff = 0, Gtot = 0;
+    DBuf<int> part_un, part_um;
   } dist;
   // ---- compacted-slice tiles + TMA ring kernel (admm_kernel_csl.cuh); enabled when every tile fits a ring stage
   struct Csl {
@@ -175,7 +179,8 @@ struct Work {
     DBuf<unsigned char> blobN, blobM;
     DBuf<int> srcN1, srcN2, srcM, part_tn, part_tm;
     DBuf<long long> cta_ns;      // B200QP_DEBUG_CTA=1: per-CTA work time of the B / C phases
-    int ntilesN = 0, ntilesM = 0, S = 0, capb = 0, G = 1, un = 4, um = 4;
+    int ntilesN = 0, ntilesM = 0, S = 0, capb = 0, G = 1, un = 4, um = 4, max_coop = 1;
+    std::vector<unsigned> h_toffN, h_toffM;   // host copies of the tile offsets (the multi-GPU setup re-partitions)
     size_t smem = 0;
     double bytesN = 0, bytesM = 0;   // blob bytes of the two tile streams (engine byte model)
   } csl;
@@ -201,6 +206,7 @@ struct Work {
     if (dist.region) cudaFree(dist.region);
     dist.xtot.free(); dist.release.free();
     dist.part_m.free(); dist.part_slice.free(); dist.part_uni.free(); dist.part_mall.free();
+    dist.part_un.free(); dist.part_um.free();
     if (h_x) cudaFreeHost(h_x);
     if (h_y) cudaFreeHost(h_y);
     if (h_pc) cudaFreeHost(h_pc);
@@ -214,19 +220,23 @@ struct Work {
 // shared-region layout of a multi-GPU rank (same offsets on every rank): control block, arrival flags, barrier
 // payload, then the five gathered vectors -- w, w2, y (length m) and p, d (length n)
 struct RegionLayout {
-  size_t ctrl, flags, payload, wf, w2f, yf, p, d, total;
+  size_t ctrl, flags, payload, arrive, hdr, xbank, wf, w2f, yf, p, d, total;
   RegionLayout(size_t n, size_t m) {
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t o = 0;
     ctrl = o; o = al(o + sizeof(Ctrl));
     flags = o; o = al(o + MAXW * sizeof(unsigned long long));
     payload = o; o = al(o + 2 * MAXW * KMAX * sizeof(double));
+    arrive = o; o = al(o + sizeof(unsigned long long));          // tile kernel: arrivals of all CTAs of all ranks
+    hdr = o; o = al(o + 4 * sizeof(int));                        // {G of this rank, uses the tile kernel}
+    xbank = o; o = al(o + (size_t)2 * KMAX * MAXW * CSL_GMAX * sizeof(double));
     const size_t vn = al(n * sizeof(double)), vm = al(std::max<size_t>(m, 1) * sizeof(double));
     wf = o; o += vm; w2f = o; o += vm; yf = o; o += vm; p = o; o += vn; d = o; o += vn;
     total = o;
   }
 };
 
+static_assert(MAXW == CSL_MAXW, "one world-size limit");
 thread_local bool g_skip_csl = false;   // set by b200qp_dist_setup around its call of b200qp_setup (multi-GPU ranks use the CSR kernel)
 
 inline Work* W(b200qp_solver* s) { return static_cast<Work*>(s->work); }
@@ -332,6 +342,7 @@ CArgs make_cargs(Work* w) {
   c.S = w->csl.S; c.capb = w->csl.capb;
   c.cta_ns = w->csl.cta_ns.p;
   c.direct = std::getenv("B200QP_CSL_DIRECT") ? std::atoi(std::getenv("B200QP_CSL_DIRECT")) : 0;
+  c.debug = std::getenv("B200QP_CSL_DEBUG") ? std::atoi(std::getenv("B200QP_CSL_DEBUG")) : 0;
   return c;
 }
 
@@ -376,7 +387,11 @@ KArgs make_args(b200qp_solver* sv) {
   a.cg_max_iter = st->cg_max_iter; a.cg_precond = st->cg_precond == B200QP_DIAGONAL_PRECONDITIONER;
   a.rho_is_vec = st->rho_is_vec; a.check_dualgap = st->check_dualgap; a.verbose = st->verbose;
   a.polish_mode = 0;
-  if (w->dist.connected) {
+  if (w->dist.connected && w->dist.use_csl) {
+    // tile kernel: every vector keeps its full length and global indices; only the control block moves into the
+    // peer-mapped region (peers raise the abort flag there)
+    a.ctrl = (Ctrl*)(w->dist.region + RegionLayout(w->n, w->m).ctrl);
+  } else if (w->dist.connected) {
     // row slab views: A_g = rows [mlo, mhi) of CSR(A) (pointer offset) and the slab of every m-vector; A' and P
     // stay whole (the kernel walks the rows of its variable slice).  w, w2, p, d already live in the shared region
     // (borrowed at dist_setup), so the generic pointers above are the full, peer-visible copies.
@@ -425,6 +440,25 @@ XArgs make_xargs(Work* w) {
   return x;
 }
 
+XCsl make_xcsl(Work* w) {
+  XCsl x{};
+  Work::Dist& d = w->dist;
+  if (!d.use_csl) return x;
+  RegionLayout L(w->n, w->m);
+  x.rank = d.rank; x.world = d.world; x.G = d.G; x.Gtot = d.Gtot; x.goff = d.goff;
+  x.part_un = d.part_un.p; x.part_um = d.part_um.p;
+  x.epoch0 = d.xepoch;
+  for (int h = 0; h < d.world; ++h) {
+    char* b = d.peer[h];
+    x.arrive[h] = (unsigned long long*)(b + L.arrive);
+    x.xbank[h] = (double*)(b + L.xbank);
+    x.p[h] = (double*)(b + L.p); x.d[h] = (double*)(b + L.d);
+    x.w[h] = (double*)(b + L.wf); x.w2[h] = (double*)(b + L.w2f); x.y[h] = (double*)(b + L.yf);
+    x.abort_flag[h] = &((Ctrl*)(b + L.ctrl))->abort;
+  }
+  return x;
+}
+
 // launch of the persistent kernel (asynchronous); finish_admm() waits and fills w->h_out + device time
 void launch_admm(b200qp_solver* sv, const KArgs& a) {
   Work* w = W(sv);
@@ -432,6 +466,19 @@ void launch_admm(b200qp_solver* sv, const KArgs& a) {
   CK(cudaMemsetAsync(w->out.p, 0, sizeof(KOut), w->stream));
   if (w->dist.world > 1 || w->dist.connected) {
     if (!w->dist.connected || w->dist.broken) throw (int)B200QP_WORKSPACE_NOT_INIT_ERROR;
+    if (w->dist.use_csl) {
+      KArgs ac = a;
+      ac.G = w->dist.G;
+      CArgs c = make_cargs(w);
+      c.cta_ns = nullptr;
+      XCsl xc = make_xcsl(w);
+      const void* fn = b200qp_csl_kernel(true);
+      void* params[] = {(void*)&ac, (void*)&c, (void*)&xc};
+      CK(cudaEventRecord(w->ev0, w->stream));
+      CK(cudaLaunchCooperativeKernel(fn, dim3(w->dist.G), dim3(CSL_NT), params, w->csl.smem, w->stream));
+      CK(cudaEventRecord(w->ev1, w->stream));
+      return;
+    }
     CK(cudaMemsetAsync(w->dist.release.p, 0, sizeof(unsigned long long), w->stream));
     XArgs x = make_xargs(w);
     admm_dist_fn fn = pick_kernel_dist(w->dist.lgn, w->dist.lgm);
@@ -446,8 +493,9 @@ void launch_admm(b200qp_solver* sv, const KArgs& a) {
       w->csl.cta_ns.zero(w->stream);
     }
     CArgs c = make_cargs(w);
-    const void* fn = b200qp_csl_kernel();
-    void* params[] = {(void*)&ac, (void*)&c};
+    XCsl xc{};
+    const void* fn = b200qp_csl_kernel(false);
+    void* params[] = {(void*)&ac, (void*)&c, (void*)&xc};
     CK(cudaEventRecord(w->ev0, w->stream));
     CK(cudaLaunchCooperativeKernel(fn, dim3(w->csl.G), dim3(CSL_NT), params, w->csl.smem, w->stream));
   } else {
@@ -523,6 +571,45 @@ double algo_bytes_engine(const Work* w, long long iters, long long cg, int check
 }  // namespace
 
 static int polish_impl(b200qp_solver* solver);
+
+// Ring depth by measurement (single-GPU tile kernel, large problems).  Two shared-memory footprints are worth having:
+// 94 KB per CTA keeps two CTAs inside the 196 KB carve-out (60 KB of L1: the sectors of in-flight gathers wait there --
+// uniformly random columns run 1.46x faster), 108 KB takes the 228 KB carve-out with a deeper ring (sparsity with
+// locality is stream-bound and runs 1.2x faster there).  Three cold ADMM iterations are timed under each; the iterates
+// are zeroed again afterwards (setup leaves x = z = y = 0).  B200QP_RING_KB / B200QP_AUTOTUNE=0 switch it off.
+static void csl_autotune(b200qp_solver* sv) {
+  Work* w = W(sv);
+  Work::Csl& cs = w->csl;
+  if (!cs.enabled || w->dist.world > 1 || g_skip_csl) return;
+  if (std::getenv("B200QP_RING_KB")) return;
+  if (const char* e = std::getenv("B200QP_AUTOTUNE")) if (std::atoi(e) == 0) return;
+  if ((long long)cs.ntilesN + cs.ntilesM < 64LL * cs.G) return;          // small problems: nothing to gain
+  const size_t budgets[2] = {CSL_RING_BUDGET, CSL_RING_BUDGET_DEEP};
+  int S_of[2]; float ms_of[2] = {0.f, 0.f};
+  for (int c = 0; c < 2; ++c) S_of[c] = (int)std::min<size_t>(32, budgets[c] / cs.capb);
+  if (S_of[1] <= S_of[0]) return;
+  const b200qp_settings keep = *sv->settings;
+  sv->settings->max_iter = 3; sv->settings->check_termination = 0; sv->settings->adaptive_rho = 0;
+  sv->settings->time_limit = 1e9; sv->settings->verbose = 0;
+  for (int c = 0; c < 2; ++c) {
+    cs.S = S_of[c]; cs.smem = (size_t)cs.S * cs.capb;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, b200qp_csl_kernel(false), CSL_NT, cs.smem));
+    if (occ * w->stats.grid < cs.G && occ * 148 < cs.G) { ms_of[c] = 1e30f; continue; }    // cannot be co-resident
+    for (int rep = 0; rep < 2; ++rep) {
+      w->x.zero(w->stream); w->z.zero(w->stream); w->y.zero(w->stream);
+      KArgs a = make_args(sv);
+      run_admm(sv, a, &ms_of[c]);
+      if (w->h_out.aborted) { ms_of[c] = 1e30f; break; }
+    }
+  }
+  *sv->settings = keep;
+  const int best = ms_of[1] < 0.95f * ms_of[0] ? 1 : 0;      // the deep ring must win clearly
+  cs.S = S_of[best]; cs.smem = (size_t)cs.S * cs.capb;
+  w->stats.autotune_ms[0] = ms_of[0]; w->stats.autotune_ms[1] = ms_of[1];
+  w->x.zero(w->stream); w->z.zero(w->stream); w->y.zero(w->stream);
+  CK(cudaStreamSynchronize(w->stream));
+}
 
 // ================================================================================ C ABI
 extern "C" {
@@ -815,11 +902,15 @@ b200qp_int b200qp_setup(b200qp_solver** solverp, const b200qp_csc* P, const b200
         const void* fn = b200qp_csl_kernel();
         // a per-function attribute shared by every solver of the process: always the full budget (a per-solver value
         // would race between solvers that are set up from different threads)
-        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ring_budget, CSL_RING_BUDGET)));
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ring_budget, CSL_RING_BUDGET_DEEP)));
+        CK(cudaFuncSetAttribute(b200qp_csl_kernel(true), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)std::max(ring_budget, CSL_RING_BUDGET_DEEP)));
         int occ2 = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fn, CSL_NT, cs.smem));
         if (occ2 >= 1) {
           const int max_coop = occ2 * prop.multiProcessorCount;
+          cs.max_coop = max_coop;
+          cs.h_toffN = HN.toff; cs.h_toffM = HM.toff;
           long long wantG = ((long long)HN.ntiles + HM.ntiles) / 16;
           if (const char* e = std::getenv("B200QP_GRID")) wantG = std::atoll(e);
           cs.G = (int)std::min<long long>(std::max<long long>(wantG, 1), max_coop);
@@ -857,6 +948,7 @@ b200qp_int b200qp_setup(b200qp_solver** solverp, const b200qp_csc* P, const b200
     CK(cudaStreamSynchronize(s));
     w->stats.n = n; w->stats.m = m; w->stats.nnzP_full = w->P.nnz; w->stats.nnzA = w->A.nnz;
     w->stats.grid = w->csl.enabled ? w->csl.G : w->G; w->stats.block = w->csl.enabled ? CSL_NT : NT;
+    csl_autotune(sv);
   } catch (int code) {
     b200qp_cleanup(sv);
     return code;
@@ -945,7 +1037,7 @@ static b200qp_int solve_end(b200qp_solver* solver) {
     w->stats.algo_bytes_engine = algo_bytes_engine(w, o.iter, o.cg_iters, st->check_termination);
     w->stats.spmv_bytes[0] = spmv_bytes(w->A.nnz, w->m, w->n);
     w->stats.spmv_bytes[1] = spmv_bytes(w->P.nnz, w->n, w->n) + spmv_bytes(w->A.nnz, w->n, w->m);
-    w->stats.kernel_kind = w->dist.connected ? 2 : (w->csl.enabled ? 1 : 0);
+    w->stats.kernel_kind = w->dist.connected ? (w->dist.use_csl ? 3 : 2) : (w->csl.enabled ? 1 : 0);
     w->stats.ring_stages = w->csl.enabled ? w->csl.S : 0;
     w->stats.ring_stage_bytes = w->csl.enabled ? w->csl.capb : 0;
     if (w->dist.connected) { w->stats.grid = w->dist.G; }
@@ -1352,7 +1444,10 @@ b200qp_int b200qp_dist_setup(b200qp_solver** solverp, b200qp_int rank, b200qp_in
   if (world < 1 || world > MAXW || rank < 0 || rank >= world) return B200QP_DATA_VALIDATION_ERROR;
   b200qp_settings st = *settings;
   if (rank != 0) st.verbose = 0;
-  g_skip_csl = true;
+  {
+    const char* fmt = std::getenv("B200QP_DIST_FORMAT");
+    g_skip_csl = fmt && std::string(fmt) == "csr";      // default: the tile kernel, when the matrices fit its tiles
+  }
   int err = b200qp_setup(solverp, P, q, A, l, u, m, n, &st);
   g_skip_csl = false;
   if (err) return err;
@@ -1412,8 +1507,37 @@ b200qp_int b200qp_dist_setup(b200qp_solver** solverp, b200qp_int rank, b200qp_in
     d.part_uni.alloc(d.G + 1); d.part_uni.upload(pu.data(), d.G + 1, s);
     d.part_mall.alloc(d.G + 1); d.part_mall.upload(pa.data(), d.G + 1, s);
     w->red.alloc((size_t)2 * KMAX * std::max(d.G, w->G)); w->red.zero(s);
+    if (w->csl.enabled) {
+      // ---- tile kernel over the ranks: tile ranges per rank (balanced by tile bytes), then per CTA of the rank
+      Work::Csl& cs = w->csl;
+      d.use_csl = true;
+      long long want = ((long long)cs.ntilesN + cs.ntilesM) / std::max(1, (int)world) / 16;
+      if (const char* e = std::getenv("B200QP_GRID")) want = std::atoll(e);
+      const int cap = std::min(CSL_GMAX, std::max(1, cs.max_coop / std::max(1, (int)ranks_on_device)));
+      d.G = (int)std::min<long long>(std::max<long long>(want, 1), cap);
+      std::vector<int> rn, rm, ptn, ptm, pun(d.G + 1), pum(d.G + 1);
+      csl_partition_range(cs.h_toffN, 0, cs.ntilesN, world, rn);
+      csl_partition_range(cs.h_toffM, 0, cs.ntilesM, world, rm);
+      csl_partition_range(cs.h_toffN, rn[rank], rn[rank + 1], d.G, ptn);
+      csl_partition_range(cs.h_toffM, rm[rank], rm[rank + 1], d.G, ptm);
+      for (int g = 0; g <= d.G; ++g) { pun[g] = (int)((long long)n * g / d.G); pum[g] = (int)((long long)m * g / d.G); }
+      cs.part_tn.free(); cs.part_tm.free();
+      cs.part_tn.alloc(ptn.size()); cs.part_tn.upload(ptn.data(), ptn.size(), s);
+      cs.part_tm.alloc(ptm.size()); cs.part_tm.upload(ptm.data(), ptm.size(), s);
+      d.part_un.alloc(pun.size()); d.part_un.upload(pun.data(), pun.size(), s);
+      d.part_um.alloc(pum.size()); d.part_um.upload(pum.data(), pum.size(), s);
+      d.mlo = std::min(rm[rank] * 32, (int)m); d.mhi = std::min(rm[rank + 1] * 32, (int)m);
+      for (int h = 0; h <= world; ++h) d.slice[h] = std::min(rn[h] * 32, (int)n);
+      // y joins the peer-mapped vectors: the Z phase of a check iteration pushes it, so at exit every rank holds all of y
+      w->y.borrow((double*)(d.region + L.yf), m);
+      w->red.alloc((size_t)2 * KMAX * std::max(std::max(d.G, w->G), cs.G)); w->red.zero(s);
+    }
+    {   // what the peers need to know about this rank, read by them at connect time
+      const int hdr[4] = {d.G, d.use_csl ? 1 : 0, 0, 0};
+      CK(cudaMemcpyAsync(d.region + L.hdr, hdr, sizeof(hdr), cudaMemcpyHostToDevice, s));
+    }
     CK(cudaStreamSynchronize(s));
-    if (world == 1) d.connected = true;
+    if (world == 1) { d.goff = 0; d.Gtot = d.G; d.connected = true; }
   } catch (int code) {
     b200qp_cleanup(sv);
     *solverp = nullptr;
@@ -1425,8 +1549,9 @@ b200qp_int b200qp_dist_setup(b200qp_solver** solverp, b200qp_int rank, b200qp_in
 b200qp_int b200qp_dist_row_range(const b200qp_solver* solver, b200qp_int* mlo, b200qp_int* mhi) {
   if (!solver || !solver->work) return B200QP_WORKSPACE_NOT_INIT_ERROR;
   const Work* w = W(solver);
-  if (mlo) *mlo = w->dist.region ? w->dist.mlo : 0;
-  if (mhi) *mhi = w->dist.region ? w->dist.mhi : w->m;
+  // tile kernel: y and the primal certificate are complete on every rank at exit (pushed by the last check iteration)
+  if (mlo) *mlo = (w->dist.region && !w->dist.use_csl) ? w->dist.mlo : 0;
+  if (mhi) *mhi = (w->dist.region && !w->dist.use_csl) ? w->dist.mhi : w->m;
   return 0;
 }
 
@@ -1441,6 +1566,21 @@ b200qp_int b200qp_dist_get_handle(b200qp_solver* solver, void* handle64) {
     std::memcpy(handle64, &h, 64);
   } catch (int code) { return code; }
   return 0;
+}
+
+// every rank published {G, uses the tile kernel} in its region header at setup: bank offsets of the flat barrier
+static void dist_read_peers(Work* w) {
+  Work::Dist& d = w->dist;
+  RegionLayout L(w->n, w->m);
+  int goff = 0, gtot = 0;
+  for (int h = 0; h < d.world; ++h) {
+    int hdr[4] = {0, 0, 0, 0};
+    CK(cudaMemcpy(hdr, d.peer[h] + L.hdr, sizeof(hdr), cudaMemcpyDefault));
+    if ((hdr[1] != 0) != d.use_csl || hdr[0] < 1 || hdr[0] > CSL_GMAX) throw (int)B200QP_DATA_VALIDATION_ERROR;
+    if (h == d.rank) goff = gtot;
+    gtot += hdr[0];
+  }
+  d.goff = goff; d.Gtot = gtot;
 }
 
 // multi-process: handles = world x 64 bytes, in rank order (exchanged by the caller, e.g. torch.distributed)
@@ -1459,6 +1599,7 @@ b200qp_int b200qp_dist_connect_ipc(b200qp_solver* solver, const void* handles) {
       d.peer[h] = (char*)ptr;
       d.opened[h] = true;
     }
+    dist_read_peers(w);
     d.connected = true;
   } catch (int code) { return code; }
   return 0;
@@ -1485,6 +1626,11 @@ b200qp_int b200qp_dist_connect_local(b200qp_solver** group, b200qp_int world) {
         }
         wa->dist.peer[b] = wb->dist.region;
       }
+    }
+    for (int a = 0; a < world; ++a) {
+      Work* wa = W(group[a]);
+      CK(cudaSetDevice(wa->device));
+      dist_read_peers(wa);
       wa->dist.connected = true;
     }
   } catch (int code) { return code; }

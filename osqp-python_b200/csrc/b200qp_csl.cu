@@ -58,7 +58,9 @@ k_spmv_csl(const CslStream M, const int* __restrict__ part, int S, int capb, con
 
 }  // namespace b200qp
 
-const void* b200qp_csl_kernel() { return (const void*)b200qp::admm_kernel_csl; }
+const void* b200qp_csl_kernel(bool dist) {
+  return dist ? (const void*)b200qp::admm_kernel_csl<true> : (const void*)b200qp::admm_kernel_csl<false>;
+}
 
 void b200qp_spmv_csl_launch(const b200qp::CslStream& M, const int* part, int G, int S, int capb, size_t smem, const double* x,
                             double* y, cudaStream_t stream) {

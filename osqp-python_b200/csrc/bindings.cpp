@@ -189,7 +189,8 @@ class Solver {
                     "block"_a = st.block, "n"_a = st.n, "m"_a = st.m, "nnzP_full"_a = st.nnzP_full, "nnzA"_a = st.nnzA,
                     "algo_bytes_engine"_a = st.algo_bytes_engine, "spmv_bytes_A"_a = st.spmv_bytes[0],
                     "spmv_bytes_K"_a = st.spmv_bytes[1], "kernel_kind"_a = st.kernel_kind,
-                    "ring_stages"_a = st.ring_stages, "ring_stage_bytes"_a = st.ring_stage_bytes);
+                    "ring_stages"_a = st.ring_stages, "ring_stage_bytes"_a = st.ring_stage_bytes,
+                    "autotune_ms"_a = py::make_tuple(st.autotune_ms[0], st.autotune_ms[1]));
   }
 
  private:

@@ -113,4 +113,22 @@ inline void csl_partition(const CslHost& H, int G, std::vector<int>& part) {
   part[G] = H.ntiles;
 }
 
+// the same over the tile sub-range [t_lo, t_hi) (multi-GPU: rank ranges first, then the CTAs of a rank); toff = tile
+// offsets in 16-byte units (CslHost::toff); part receives G + 1 absolute tile numbers
+inline void csl_partition_range(const std::vector<unsigned>& toff, int t_lo, int t_hi, int G, std::vector<int>& part) {
+  part.assign(G + 1, t_hi);
+  part[0] = t_lo;
+  const int T = t_hi - t_lo;
+  if (T <= 0) { std::fill(part.begin(), part.end(), t_lo); return; }
+  std::vector<long long> pre(T + 1, 0);
+  for (int t = 0; t < T; ++t) pre[t + 1] = pre[t] + 16LL * (toff[t_lo + t + 1] - toff[t_lo + t]) + 512;
+  int t = 0;
+  for (int g = 1; g < G; ++g) {
+    const long long target = pre[T] * g / G;
+    t = (int)(std::lower_bound(pre.begin() + t, pre.end(), target) - pre.begin());
+    part[g] = t_lo + std::min(t, T);
+  }
+  part[G] = t_hi;
+}
+
 }  // namespace b200qp
