@@ -245,6 +245,7 @@ def structured_line(args, peak):
                        f"diagonal (banded), seed {SEED}; cold-start solve() to eps 1e-3",
            "value": iters / (dev_ms * 1e-3), "unit": UNIT, "ms_per_step": dev_ms / steps, "steps": steps,
            "admm_iters_per_step": iters // steps, "pcg_iters_per_admm_iter": cg / max(iters, 1), "status": res.info.status,
+           "ring": f"{st['ring_stages']} stages x {st['ring_stage_bytes']} B", "ring_autotune_ms": list(st.get("autotune_ms", (0, 0))),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "frac_of_8TBs": achieved / 8000.0}}
     if not args.no_spmv:
@@ -313,6 +314,7 @@ def run_ours(args):
         "detail": {"admm_iters_per_step": iters // args.steps, "pcg_iters_per_admm_iter": cg / max(iters, 1), "status": status,
                    "phase_ms_per_step": dict(zip(names, [round(v / args.steps, 3) for v in phases])),
                    "grid": f"{st['grid']}x{st['block']}", "ring": f"{st['ring_stages']} stages x {st['ring_stage_bytes']} B" if tile else None,
+                   "ring_autotune_ms": list(st.get("autotune_ms", (0, 0))),
                    "setup_s": t_setup, "problem_gen_s": t_gen},
         "roofline": {"bound": "hbm", "kernel": kernel,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

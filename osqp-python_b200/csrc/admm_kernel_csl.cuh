@@ -24,7 +24,6 @@
 //   B  m-tiles: t = rho .* (A u)         C  n-tiles: w = P u + sigma u + A' t, <w,u>
 //   V  n-elements: p, s, d, r, u = M^-1 r, <r,u>, |r|inf       (128-bit loads / stores)
 #pragma once
-#include <cstdio>
 #include <type_traits>
 
 #include "admm_kernel.cuh"
@@ -166,36 +165,6 @@ __device__ __forceinline__ double part_dot_sq(const int* ip, const double* vp, i
   return s;
 }
 
-// CTA-level reduction helpers for a CTA of NWARPS warps (device_common.cuh hard-wires NW = 16)
-template <int K, int NWARPS>
-__device__ __forceinline__ void block_reduce_store_w(double (&v)[K], unsigned maxmask, double* bank, int G, double* s_red) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const double r = warp_combine(v[k], (maxmask >> k) & 1u);
-    if (lane == 0) s_red[k * NWARPS + warp] = r;
-  }
-  __syncthreads();
-  if (threadIdx.x < K) {
-    const bool mx = (maxmask >> threadIdx.x) & 1u;
-    double acc = s_red[threadIdx.x * NWARPS];
-    for (int w = 1; w < NWARPS; ++w) acc = combine(acc, s_red[threadIdx.x * NWARPS + w], mx);
-    bank[threadIdx.x * G + blockIdx.x] = acc;
-  }
-}
-template <int K, int NWARPS>
-__device__ __forceinline__ void grid_reduce_load_w(const double* bank, int G, unsigned maxmask, double* s_tot) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = warp; k < K; k += NWARPS) {
-    const bool mx = (maxmask >> k) & 1u;
-    double acc = mx ? __longlong_as_double(0xfff0000000000000LL) : 0.0;
-    for (int c = lane; c < G; c += 32) acc = combine(acc, __ldcg(bank + k * G + c), mx);
-    acc = warp_combine(acc, mx);
-    if (lane == 0) s_tot[k] = acc;
-  }
-  __syncthreads();
-}
-
 // After the barrier: every CTA folds all Gt partials of every slot with ALL its threads (thread t takes t, t + NT, ...;
 // warp butterfly; warps in order) -- one L2 round trip per slot whatever Gt is (8 GPUs: 2368 partials), fixed order.
 template <int K, int NWARPS>
@@ -327,7 +296,6 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
             else if (now - t0 > 10000000000ULL) { ok = 0; break; }   // 10 s watchdog
           }
         }
-        if (*(volatile int*)&a.ctrl->abort) ok = 0;
         if (!ok) {     // tell everybody, so that no rank spins until its own watchdog
 #pragma unroll
           for (int h = 0; h < CSL_MAXW; ++h) if (h < x.world) *(volatile int*)x.abort_flag[h] = 1;
@@ -399,20 +367,14 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
       const int nt = min(31, i1 - ib);
       for (int i = 0; i < nt; ++i) {
         const unsigned o0 = __shfl_sync(0xffffffffu, mine, i), o1 = __shfl_sync(0xffffffffu, mine, i + 1);
-        int alive = 1;
         if (lane == 0) {
           const int stg = q >= S ? q - S : q;
           const unsigned par = q >= S ? 1u : 0u;
-          if (!mbar_wait_guard(&bar_empty[stg], par, &a.ctrl->abort)) {   // previous occupant released (or the initial arrival)
-            if (c.debug) printf("[b200qp csl] producer timeout: cta %d stage %d q %d tile %d of [%d,%d) q0 %d S %d epoch %llu\n", cta, stg, q, ib + i, i0, i1, q0, S, sync.epoch);
-            alive = 0;
-          } else {
-            const uint32_t bytes = (o1 - o0) * 16u;
-            mbar_expect_tx(&bar_full[stg], bytes);
-            bulk_g2s_hint(ring + (size_t)stg * c.capb, st.blob + (size_t)o0 * 16u, bytes, &bar_full[stg], pol);
-          }
+          mbar_wait(&bar_empty[stg], par);          // previous occupant released (or the initial arrival)
+          const uint32_t bytes = (o1 - o0) * 16u;
+          mbar_expect_tx(&bar_full[stg], bytes);
+          bulk_g2s_hint(ring + (size_t)stg * c.capb, st.blob + (size_t)o0 * 16u, bytes, &bar_full[stg], pol);
         }
-        if (!__shfl_sync(0xffffffffu, alive, 0)) return;     // the abort flag is up: the next barrier ends the kernel
         q = q + 1 == 2 * S ? 0 : q + 1;
         __syncwarp();
       }
@@ -441,10 +403,7 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
       int q = q_add(q0, warp);
       for (int i = warp; i < T; i += CSL_NWC) {
         const int stg = q >= S ? q - S : q;
-        if (!__all_sync(0xffffffffu, mbar_wait_guard(&bar_full[stg], q >= S ? 1u : 0u, &a.ctrl->abort))) {
-          if (c.debug && lane == 0) printf("[b200qp csl] consumer timeout: cta %d warp %d stage %d q %d tile %d of %d q0 %d S %d epoch %llu pre %d\n", cta, warp, stg, q, i, T, q0, S, sync.epoch, pre_issued);
-          break;
-        }
+        mbar_wait(&bar_full[stg], q >= S ? 1u : 0u);
         const TileView tv = tile_view<true>(ring + (size_t)stg * c.capb, lane);
         body(t0 + i, tv, [&] { __syncwarp(); if (lane == 0) csl_mbar_arrive(&bar_empty[stg]); }, std::true_type{});
         q = q_add(q, CSL_NWC);
@@ -458,7 +417,7 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
     if (producer && lane == 0)
       for (int i = 0; i < pre_issued; ++i) {
         const int q = q_add(ring_q, i);
-        if (!mbar_wait_guard(&bar_full[q >= S ? q - S : q], q >= S ? 1u : 0u, &a.ctrl->abort)) break;
+        mbar_wait(&bar_full[q >= S ? q - S : q], q >= S ? 1u : 0u);
       }
   };
 #define CSL_DIE() do { if (cta == 0 && tid == 0) a.out->aborted = 1; return; } while (0)

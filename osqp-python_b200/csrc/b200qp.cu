@@ -342,7 +342,6 @@ CArgs make_cargs(Work* w) {
   c.S = w->csl.S; c.capb = w->csl.capb;
   c.cta_ns = w->csl.cta_ns.p;
   c.direct = std::getenv("B200QP_CSL_DIRECT") ? std::atoi(std::getenv("B200QP_CSL_DIRECT")) : 0;
-  c.debug = std::getenv("B200QP_CSL_DEBUG") ? std::atoi(std::getenv("B200QP_CSL_DEBUG")) : 0;
   return c;
 }
 

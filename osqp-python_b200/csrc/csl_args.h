@@ -25,7 +25,6 @@ struct CArgs {                   // what the CSL kernel needs beyond KArgs
   double *ps, *ss;               // n-vectors: PCG search direction and K * direction
   int S, capb;                   // ring: stages and bytes per stage
   int direct;                    // diagnostics: 1 = no TMA ring, plain loads of the tiles
-  int debug;                     // B200QP_CSL_DEBUG=1: a ring wait that times out prints who waited for what
   long long* cta_ns;             // optional [G][2]: per-CTA time inside the B / C phases before the barrier (diagnostics)
 };
 

@@ -17,4 +17,4 @@ for i in range(int(os.environ.get("REPS", 4))):
         break
     st = prob.stats()
     print("solve", i, res.info.status, res.info.iter, "cg", st["cg_iters"], "kernel_ms %.2f" % st["kernel_ms"], "wall %.2f" % (time.perf_counter() - t),
-          "ring", st["ring_stages"], st["ring_stage_bytes"], "grid", st["grid"], flush=True)
+          "ring", st["ring_stages"], st["ring_stage_bytes"], "grid", st["grid"], "autotune", st.get("autotune_ms"), flush=True)
