@@ -199,8 +199,8 @@ __device__ __forceinline__ void csl_st_sys(double* p, double v) {
 __device__ __forceinline__ void csl_st_sys2(double2* p, double2 v) {
   asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
-__device__ __forceinline__ void csl_red_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void csl_st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long csl_ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
@@ -273,22 +273,28 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
     } else {
       __syncthreads();                       // every thread's stores of this phase (pushes included) are issued
       sync.epoch++;
+      const unsigned long long e = x.epoch0 + sync.epoch;
+      // arrival: one flag per CTA per rank, written with a release store (cumulative: the CTA's earlier peer stores --
+      // pushes and partials -- are visible before it).  No atomics: 296 remote atomics on one address serialise in the
+      // peer's L2 (measured: 17-20 us per barrier; a two-level barrier with a last-arriver hand-off: 25 us), 296 stores to
+      // 296 addresses pipeline over NVLink (10-12 us, most of it the system-scope fence of the release).
       if (tid < CSL_MAXW && tid < x.world) {
-        unsigned long long* dst = x.arrive[0];
+        unsigned long long* dst = x.xflag[0];
 #pragma unroll
-        for (int h = 1; h < CSL_MAXW; ++h) if (tid == h) dst = x.arrive[h];
-        __threadfence_system();              // cumulative: orders the CTA's earlier peer stores before the arrival
-        csl_red_release_sys(dst, 1ULL);
+        for (int h = 1; h < CSL_MAXW; ++h) if (tid == h) dst = x.xflag[h];
+        csl_st_release_sys(dst + x.goff + cta, e);
       }
-      if (tid == 0) {
-        const unsigned long long* mine = x.arrive[0];
+      // wait: thread t watches flags t, t + NT, ... of MY rank's array (the peers' CTAs write there) with acquire loads.
+      // (Measured alternatives: relaxed polls + one system fence per thread 2x slower -- concurrent MEMBAR.SYS are what
+      // costs; warp 0 polling all flags with a back-off 5x slower.)
+      const unsigned long long* mine = x.xflag[0];
 #pragma unroll
-        for (int h = 1; h < CSL_MAXW; ++h) if (x.rank == h) mine = x.arrive[h];
-        const unsigned long long target = (x.epoch0 + sync.epoch) * (unsigned long long)x.Gtot;
-        int ok = 1;
+      for (int h = 1; h < CSL_MAXW; ++h) if (x.rank == h) mine = x.xflag[h];
+      int ok = 1;
+      for (int f = tid; f < x.Gtot; f += CSL_NT) {
         unsigned spins = 0;
         unsigned long long t0 = 0;
-        while (csl_ld_acquire_sys(mine) < target) {
+        while (csl_ld_acquire_sys(mine + f) < e) {
           if ((++spins & 0x3ffu) == 0) {
             if (*(volatile int*)&a.ctrl->abort) { ok = 0; break; }
             const unsigned long long now = global_timer_ns();
@@ -296,14 +302,14 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
             else if (now - t0 > 10000000000ULL) { ok = 0; break; }   // 10 s watchdog
           }
         }
-        if (!ok) {     // tell everybody, so that no rank spins until its own watchdog
-#pragma unroll
-          for (int h = 0; h < CSL_MAXW; ++h) if (h < x.world) *(volatile int*)x.abort_flag[h] = 1;
-        }
-        s_ok = ok;
+        if (!ok) break;
       }
-      __syncthreads();
-      return s_ok != 0;
+      ok = __syncthreads_and(ok);
+      if (!ok && tid == 0) {     // tell everybody, so that no rank spins until its own watchdog
+#pragma unroll
+        for (int h = 0; h < CSL_MAXW; ++h) if (h < x.world) *(volatile int*)x.abort_flag[h] = 1;
+      }
+      return ok != 0;
     }
   };
   // CTA partials of K slots -> the bank every CTA will fold after the next barrier (on every rank when DIST)

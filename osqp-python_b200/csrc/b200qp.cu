@@ -227,7 +227,7 @@ struct RegionLayout {
     ctrl = o; o = al(o + sizeof(Ctrl));
     flags = o; o = al(o + MAXW * sizeof(unsigned long long));
     payload = o; o = al(o + 2 * MAXW * KMAX * sizeof(double));
-    arrive = o; o = al(o + sizeof(unsigned long long));          // tile kernel: arrivals of all CTAs of all ranks
+    arrive = o; o = al(o + (size_t)MAXW * CSL_GMAX * sizeof(unsigned long long));   // tile kernel: one flag per CTA of the job
     hdr = o; o = al(o + 4 * sizeof(int));                        // {G of this rank, uses the tile kernel}
     xbank = o; o = al(o + (size_t)2 * KMAX * MAXW * CSL_GMAX * sizeof(double));
     const size_t vn = al(n * sizeof(double)), vm = al(std::max<size_t>(m, 1) * sizeof(double));
@@ -449,7 +449,7 @@ XCsl make_xcsl(Work* w) {
   x.epoch0 = d.xepoch;
   for (int h = 0; h < d.world; ++h) {
     char* b = d.peer[h];
-    x.arrive[h] = (unsigned long long*)(b + L.arrive);
+    x.xflag[h] = (unsigned long long*)(b + L.arrive);
     x.xbank[h] = (double*)(b + L.xbank);
     x.p[h] = (double*)(b + L.p); x.d[h] = (double*)(b + L.d);
     x.w[h] = (double*)(b + L.wf); x.w2[h] = (double*)(b + L.w2f); x.y[h] = (double*)(b + L.yf);

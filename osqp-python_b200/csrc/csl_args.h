@@ -42,7 +42,7 @@ struct XCsl {
   int G, Gtot, goff;                         // my CTAs, CTAs of all ranks, my first slot in the banks
   const int *part_un, *part_um;              // uniform CTA partitions of [0, n) (replicated x) and [0, m) (rho re-typing)
   unsigned long long epoch0;                 // cross-GPU barriers completed by earlier launches (counters are never reset)
-  unsigned long long* arrive[CSL_MAXW];      // rank h's arrival counter
+  unsigned long long* xflag[CSL_MAXW];       // rank h's arrival flags, one per CTA of the job [Gtot]
   double* xbank[CSL_MAXW];                   // rank h's reduction banks [2][KMAX][Gtot]
   double *p[CSL_MAXW], *d[CSL_MAXW], *w[CSL_MAXW], *w2[CSL_MAXW], *y[CSL_MAXW];
   int* abort_flag[CSL_MAXW];
