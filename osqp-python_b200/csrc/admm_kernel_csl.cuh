@@ -202,6 +202,15 @@ __device__ __forceinline__ void csl_st_sys2(double2* p, double2 v) {
 __device__ __forceinline__ void csl_st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// 16-byte {value, epoch} slots: one aligned vector store / load each, so a reader that sees the epoch sees the value
+__device__ __forceinline__ void csl_st_slot(void* p, double v, unsigned long long e) {
+  asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(e) : "memory");
+}
+__device__ __forceinline__ void csl_ld_slot(const void* p, double& v, unsigned long long& e) {
+  long long bits;
+  asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(e) : "l"(p) : "memory");
+  v = __longlong_as_double(bits);
+}
 __device__ __forceinline__ unsigned long long csl_ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -350,6 +359,84 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
     }
     grid_reduce_load_all<K, CSL_NW>(bk, Gt, maxmask, s_tot, s_red);
   };
+  // A barrier whose phase pushed nothing (C: only <w,u> leaves the CTA) needs no release fence at all: every CTA writes
+  // its partial as a self-validating {value, barrier number} slot into every rank's slot array and every CTA folds the
+  // slots as they turn up -- one NVLink hop, no MEMBAR.SYS.  Having every partial also means every CTA of the job has
+  // finished the phase (a CTA stores its partial after its last tile), which is all the next phase relies on: V only
+  // touches the CTA's own elements of w, and overwrites u only after every gather of the old u has returned.
+  auto barrier_payload = [&](auto& v, auto k_tag, unsigned maxmask) -> bool {
+    constexpr int K = decltype(k_tag)::value;
+    static_assert(K <= 2, "slot array holds two slots");
+    if constexpr (!DIST) {
+      reduce_store(v, k_tag, maxmask);
+      if (!barrier()) return false;
+      reduce_load(k_tag, maxmask);
+      return true;
+    } else {
+      const unsigned long long e = x.epoch0 + sync.epoch + 1ULL;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double r = warp_combine(v[k], (maxmask >> k) & 1u);
+        if (lane == 0) s_red[k * CSL_NW + warp] = r;
+      }
+      __syncthreads();
+      if (tid < K) {
+        const bool mx = (maxmask >> tid) & 1u;
+        double acc = s_red[tid * CSL_NW];
+        for (int w = 1; w < CSL_NW; ++w) acc = combine(acc, s_red[tid * CSL_NW + w], mx);
+        const size_t off = ((size_t)tid * x.Gtot + x.goff + cta) * 16;
+#pragma unroll
+        for (int h = 0; h < CSL_MAXW; ++h) if (h < x.world) csl_st_slot(x.xslot[h] + off, acc, e);
+      }
+      sync.epoch++;
+      const unsigned char* mine = x.xslot[0];
+#pragma unroll
+      for (int h = 1; h < CSL_MAXW; ++h) if (x.rank == h) mine = x.xslot[h];
+      int ok = 1;
+      double acc[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const bool mx = (maxmask >> k) & 1u;
+        acc[k] = mx ? NEG_INF : 0.0;
+        for (int cc = tid; cc < x.Gtot && ok; cc += CSL_NT) {
+          const unsigned char* sp = mine + ((size_t)k * x.Gtot + cc) * 16;
+          double val; unsigned long long ep;
+          unsigned spins = 0;
+          unsigned long long t0 = 0;
+          for (;;) {
+            csl_ld_slot(sp, val, ep);
+            if (ep == e) break;
+            if ((++spins & 0x3ffu) == 0) {
+              if (*(volatile int*)&a.ctrl->abort) { ok = 0; break; }
+              const unsigned long long now = global_timer_ns();
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > 10000000000ULL) { ok = 0; break; }
+            }
+          }
+          if (ok) acc[k] = combine(acc[k], val, mx);
+        }
+      }
+      __syncthreads();                       // s_red is free again (the partial stores above read it)
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double r = warp_combine(acc[k], (maxmask >> k) & 1u);
+        if (lane == 0) s_red[k * CSL_NW + warp] = r;
+      }
+      ok = __syncthreads_and(ok);
+      if (tid < K) {
+        const bool mx = (maxmask >> tid) & 1u;
+        double t = s_red[tid * CSL_NW];
+        for (int w = 1; w < CSL_NW; ++w) t = combine(t, s_red[tid * CSL_NW + w], mx);
+        s_tot[tid] = t;
+      }
+      __syncthreads();
+      if (!ok && tid == 0) {
+#pragma unroll
+        for (int h = 0; h < CSL_MAXW; ++h) if (h < x.world) *(volatile int*)x.abort_flag[h] = 1;
+      }
+      return ok != 0;
+    }
+  };
   // all-gather by stores: the producing thread writes its element into every peer's copy
 #define CSL_PUSH(tab, i, v) do { if constexpr (DIST) { _Pragma("unroll") for (int h_ = 0; h_ < CSL_MAXW; ++h_) if (h_ < x.world && h_ != x.rank) csl_st_sys(x.tab[h_] + (i), (v)); } } while (0)
 #define CSL_PUSH2(tab, i2, v) do { if constexpr (DIST) { _Pragma("unroll") for (int h_ = 0; h_ < CSL_MAXW; ++h_) if (h_ < x.world && h_ != x.rank) csl_st_sys2(reinterpret_cast<double2*>(x.tab[h_]) + (i2), (v)); } } while (0)
@@ -410,7 +497,16 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
       int q = q_add(q0, warp);
       for (int i = warp; i < T; i += CSL_NWC) {
         const int stg = q >= S ? q - S : q;
-        mbar_wait(&bar_full[stg], q >= S ? 1u : 0u);
+        const unsigned par = q >= S ? 1u : 0u;
+        // An mbarrier wait sees one parity bit, so a waiter may be at most ONE phase ahead of the barrier.  The tiles of a
+        // stage go to different warps: this warp can come for use k of the stage while the fill of use k-1 (another
+        // warp's tile, issued earlier but free to land later) is still in flight -- full[stg] would then still be in
+        // phase k-1 and "parity of phase k" would read as completed: the warp would walk into a stale tile.  Waiting first
+        // for the RELEASE of use k-1 (same barrier and parity the producer waits on before it refills the stage) pins the
+        // full barrier to phase k; that wait is itself unambiguous (release k-2 precedes the issue of use k-1, which
+        // precedes every tile this warp has already consumed).  Usually long satisfied: one extra try_wait.
+        mbar_wait(&bar_empty[stg], par);
+        mbar_wait(&bar_full[stg], par);
         const TileView tv = tile_view<true>(ring + (size_t)stg * c.capb, lane);
         body(t0 + i, tv, [&] { __syncwarp(); if (lane == 0) csl_mbar_arrive(&bar_empty[stg]); }, std::true_type{});
         q = q_add(q, CSL_NWC);
@@ -728,10 +824,8 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
             v1[0] += uj * wj;
           }
         });
-        reduce_store(v1, std::integral_constant<int, 1>{}, 0u);
         if (c.cta_ns && tid == 0) c.cta_ns[2 * cta + 1] += (long long)(global_timer_ns() - tc0);
-        CSL_BARRIER_OR_DIE();
-        reduce_load(std::integral_constant<int, 1>{}, 0u);
+        if (!barrier_payload(v1, std::integral_constant<int, 1>{}, 0u)) CSL_DIE();
         mark(2);
         const double delta = s_tot[0];
         const double bj = (j == 0) ? 0.0 : gam / gam_prev;

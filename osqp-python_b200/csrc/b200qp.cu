@@ -220,7 +220,7 @@ struct Work {
 // shared-region layout of a multi-GPU rank (same offsets on every rank): control block, arrival flags, barrier
 // payload, then the five gathered vectors -- w, w2, y (length m) and p, d (length n)
 struct RegionLayout {
-  size_t ctrl, flags, payload, arrive, hdr, xbank, wf, w2f, yf, p, d, total;
+  size_t ctrl, flags, payload, arrive, hdr, xbank, xslot, wf, w2f, yf, p, d, total;
   RegionLayout(size_t n, size_t m) {
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t o = 0;
@@ -230,6 +230,7 @@ struct RegionLayout {
     arrive = o; o = al(o + (size_t)MAXW * CSL_GMAX * sizeof(unsigned long long));   // tile kernel: one flag per CTA of the job
     hdr = o; o = al(o + 4 * sizeof(int));                        // {G of this rank, uses the tile kernel}
     xbank = o; o = al(o + (size_t)2 * KMAX * MAXW * CSL_GMAX * sizeof(double));
+    xslot = o; o = al(o + (size_t)2 * MAXW * CSL_GMAX * 16);
     const size_t vn = al(n * sizeof(double)), vm = al(std::max<size_t>(m, 1) * sizeof(double));
     wf = o; o += vm; w2f = o; o += vm; yf = o; o += vm; p = o; o += vn; d = o; o += vn;
     total = o;
@@ -451,6 +452,7 @@ XCsl make_xcsl(Work* w) {
     char* b = d.peer[h];
     x.xflag[h] = (unsigned long long*)(b + L.arrive);
     x.xbank[h] = (double*)(b + L.xbank);
+    x.xslot[h] = (unsigned char*)(b + L.xslot);
     x.p[h] = (double*)(b + L.p); x.d[h] = (double*)(b + L.d);
     x.w[h] = (double*)(b + L.wf); x.w2[h] = (double*)(b + L.w2f); x.y[h] = (double*)(b + L.yf);
     x.abort_flag[h] = &((Ctrl*)(b + L.ctrl))->abort;
@@ -581,8 +583,9 @@ static void csl_autotune(b200qp_solver* sv) {
   Work::Csl& cs = w->csl;
   if (!cs.enabled || w->dist.world > 1 || g_skip_csl) return;
   if (std::getenv("B200QP_RING_KB")) return;
-  if (const char* e = std::getenv("B200QP_AUTOTUNE")) if (std::atoi(e) == 0) return;
-  if ((long long)cs.ntilesN + cs.ntilesM < 64LL * cs.G) return;          // small problems: nothing to gain
+  bool force = false;
+  if (const char* e = std::getenv("B200QP_AUTOTUNE")) { if (std::atoi(e) == 0) return; force = std::atoi(e) == 2; }
+  if (!force && (long long)cs.ntilesN + cs.ntilesM < 64LL * cs.G) return;          // small problems: nothing to gain
   const size_t budgets[2] = {CSL_RING_BUDGET, CSL_RING_BUDGET_DEEP};
   int S_of[2]; float ms_of[2] = {0.f, 0.f};
   for (int c = 0; c < 2; ++c) S_of[c] = (int)std::min<size_t>(32, budgets[c] / cs.capb);

@@ -44,6 +44,7 @@ struct XCsl {
   unsigned long long epoch0;                 // cross-GPU barriers completed by earlier launches (counters are never reset)
   unsigned long long* xflag[CSL_MAXW];       // rank h's arrival flags, one per CTA of the job [Gtot]
   double* xbank[CSL_MAXW];                   // rank h's reduction banks [2][KMAX][Gtot]
+  unsigned char* xslot[CSL_MAXW];            // rank h's {value, barrier number} slots [2][Gtot] x 16 B (fence-free barriers)
   double *p[CSL_MAXW], *d[CSL_MAXW], *w[CSL_MAXW], *w2[CSL_MAXW], *y[CSL_MAXW];
   int* abort_flag[CSL_MAXW];
 };

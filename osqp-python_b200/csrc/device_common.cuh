@@ -62,8 +62,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // Wait for a phase of an mbarrier.  One asm block with no outputs, uniform branches: the warp polls as one (the phase
 // test is a warp-level SYNCS instruction on a uniform address, every lane gets the same predicate) and the compiler
 // schedules around the block like around a single instruction.  Measured on the tile kernel: plain `bra` instead of
-// `bra.uni` costs 3 %, a C++ loop around try_wait 6-9 %.  Watchdog: a wait that lasts 5 s can only be a lost tile (ring
-// out of step); it ends in `trap` -- a launch failure on the host -- instead of a hung GPU.
+// `bra.uni` costs 3 %, a C++ loop (or any C++ branch on an output of the block) around try_wait 6-9 %.  Watchdog: a wait
+// that lasts 5 s can only be a ring out of step; it ends in `trap` -- a launch failure on the host -- instead of a hung
+// GPU.  NOTE for callers: the wait sees ONE parity bit, so a waiter may be at most one phase ahead of the barrier (see
+// the consumer loop of admm_kernel_csl.cuh for how the tile ring guarantees that).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p, q;\n\t.reg .u32 cnt;\n\t.reg .u64 t0, t1, dt;\n\t"

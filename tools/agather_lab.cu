@@ -126,6 +126,7 @@ k_spmv(const CslStream M, const int* __restrict__ part, int S, int capb, const d
   int q = warp;
   for (int i = warp; i < T; i += NWC) {
     const int stg = q >= S ? q - S : q;
+    mbar_wait(&bar_empty[stg], q >= S ? 1u : 0u);      // see admm_kernel_csl.cuh: pins full[stg] to the phase waited for
     mbar_wait(&bar_full[stg], q >= S ? 1u : 0u);
     const TileView tv = tile_view<true>(ring + (size_t)stg * capb, lane);
     double acc = 0.0;
