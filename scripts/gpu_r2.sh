@@ -32,7 +32,7 @@ if [ "${REFARM:-1}" = "1" ]; then
   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref arm rc=$?"; head -c 600 gpurun_out/bench_ref_$TAG.json
 fi
 if [ "${PROFILE:-1}" = "1" ]; then
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
+  B200QP_AUTOTUNE=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-spmv --no-batch --no-structured > gpurun_out/ncu_launch_$TAG.log 2>&1; echo "ncu launches rc=$?"
   bash scripts/ncu_traffic.sh $TAG
 fi

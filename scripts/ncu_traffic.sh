@@ -6,7 +6,7 @@
 set -u
 mkdir -p gpurun_out
 TAG=${1:-r2}
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:admm_kernel -c 1 -f -o gpurun_out/prof_admm_$TAG \
+B200QP_AUTOTUNE=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:admm_kernel -c 1 -f -o gpurun_out/prof_admm_$TAG \
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-spmv --no-batch --no-structured > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 ncu -i gpurun_out/prof_admm_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_admm_${TAG}_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_admm_$TAG.ncu-rep --page details > gpurun_out/prof_admm_${TAG}_details.txt 2>/dev/null
