@@ -339,3 +339,27 @@ def test_c3_svm_full_size_iterates_vs_oracle():
     from b200qp import problems
     P, q, A, l, u = problems.svm_qp(10_000, 40_000, density=0.01, seed=2, box_rows=20_000)
     _first_iterates_parity(P, q, A, l, u, iters=5, tol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ tile ring
+def test_second_solver_in_the_process_ring_stays_in_step():
+    """Regression for the tile ring (admm_kernel_csl.cuh, consumer loop): an mbarrier wait sees one parity bit, and a
+    consumer warp that came for use k of a stage while the fill of use k - 1 was still in flight walked into a stale
+    tile -- a hang or an illegal address, seen only on the SECOND solver of a process (bench.py's banded line after
+    the random one) once the gathers had become fast.  Config-4 size, random then banded, both kept alive; identical
+    cold solves must give identical results and the iteration counts of the single-solver runs."""
+    import osqp
+    from b200qp import problems
+    kw = dict(eps_abs=1e-3, eps_rel=1e-3, max_iter=4000, warm_starting=False, polishing=False, verbose=False)
+    keep = []
+    for band, iters in ((None, 75), (64, 75), (None, 75)):
+        P, q, A, l, u = problems.random_qp(1_000_000, 1_000_000, nnz_per_row=10, seed=3, band=band)
+        prob = osqp.OSQP(algebra="cuda")
+        prob.setup(P, q, A, l, u, **kw)
+        first = prob.solve()
+        assert first.info.status == "solved" and first.info.iter == iters, (band, first.info.status, first.info.iter)
+        for _ in range(2):
+            again = prob.solve()
+            assert again.info.status == "solved" and again.info.iter == first.info.iter
+            np.testing.assert_array_equal(again.x, first.x)
+        keep.append(prob)
