@@ -1,14 +1,16 @@
-"""One QP row-partitioned over several B200s (BASELINE.json configs[3]).
+"""One QP partitioned over several B200s (BASELINE.json configs[3]).
 
 The reference has no multi-GPU path (OSQPSettings.device is one int).  Here every rank holds the full
-problem, keeps a slab of constraint rows, and the ranks' persistent ADMM kernels exchange the partial
-A_g' w products directly over NVLink (peer-mapped memory, fused reduce-scatter + all-gather inside the
-kernel; csrc/admm_kernel_dist.cuh).  Two ways to drive it:
+problem, works on a slab of constraint rows and a slice of the variables, and the ranks' persistent ADMM
+kernels exchange the gathered vectors directly over NVLink (peer-mapped memory, all-gather by stores fused
+into the producing phases, flat flag barrier; csrc/admm_kernel_csl.cuh <true>, CSR fallback
+csrc/admm_kernel_dist.cuh).  Two ways to drive it:
 
   LocalGroup   one process, one host thread, `world` ranks (one GPU each, or several ranks sharing
                a GPU -- used by the tests to exercise the protocol on a single-GPU box).
   DistSolver   one process per GPU (torchrun); torch.distributed (NCCL) is plumbing only: it carries
-               the 64-byte cudaIpc handles once, the y slabs of the result, and the timing max.
+               the 64-byte cudaIpc handles once and the timing max (and, with the CSR fallback kernel only,
+               the y slabs of the result -- the tile kernel leaves all of y on every rank).
 """
 from types import SimpleNamespace
 
@@ -187,18 +189,22 @@ def bench(args, rank, world, local, B):
             "config": B.config_block(),
             "detail": {"admm_iters_per_step": iters // args.steps,
                        "pcg_iters_per_admm_iter": cg / max(iters, 1), "status": res.info.status,
-                       "partition": f"{world} row slabs of A + {world} variable slices of P and A'; p, d, w, w2 all-gathered by "
-                                    "NVLink stores fused into the producing phases of the persistent kernel, x replicated",
+                       "partition": f"{world} row slabs of A + {world} variable slices of P and A'; u, d, t, w2 (and y on check "
+                                    "iterations) all-gathered by NVLink stores fused into the producing phases of the persistent "
+                                    "kernel, x replicated",
+                       "kernel_kind": st.get("kernel_kind"),
                        "phase_ms_per_step_rank0": dict(zip(["R_slice_push_u", "B_Au_push_t", "C_Ku_slice", "V_slice_push_u", "x4", "Z_push_w2",
                                                             "gather_d", "x7"], [round(v / args.steps, 3) for v in phases])),
                        "grid": f"{st['grid']}x{st['block']} per GPU", "setup_s": t_setup},
-            "roofline": {"bound": "hbm", "kernel": "b200qp::admm_kernel_dist (persistent, one launch per rank per solve)",
+            "roofline": {"bound": "hbm", "kernel": ("b200qp::admm_kernel_csl<true> (tiles + TMA ring, flat NVLink barrier; persistent, one launch "
+                                                    "per rank per solve)" if st.get("kernel_kind") == 3 else
+                                                    "b200qp::admm_kernel_dist (CSR fallback; persistent, one launch per rank per solve)"),
                          "achieved": achieved / world, "peak": peak, "unit": "GB/s", "frac": achieved / world / peak,
                          "peak_source": peak_src, "traffic": None,
                          "note": "per-GPU share of the single-GPU algorithmic byte model / max-over-ranks device time"},
             "e2e": {"value": iters / (wall_ms * 1e-3), "unit": B.UNIT, "h2d_bytes_per_step": 8 * n * world,
                     "d2h_bytes_per_step": (16 * (n + m) + 128) * world, "ms_per_step": wall_ms / args.steps,
-                    "api": "DistSolver.update(q=host) + solve() -> x, y on host (y slabs all-gathered)"},
+                    "api": "DistSolver.update(q=host) + solve() -> x, y on every rank's host (complete on every rank: no gather)"},
             "gpu_launches": args.steps * 6 * world,
             "clocks": clocks,
             "cpu_baseline": {"value": None, "unit": B.UNIT, "cores": 0, "kind": "port", "sample": "N = 1 run only"},

@@ -17,8 +17,8 @@ for N in 1 2 4 8; do
 import json
 try:
     d=json.loads([l for l in open("gpurun_out/scale_${TAG}_n$N.json") if l.startswith("{")][-1])
-    print("  value", round(d["value"],1), "ms/step", round(d["ms_per_step"],1), "iters", d["config"]["admm_iters_per_step"], "kcg", round(d["config"]["pcg_iters_per_admm_iter"],2), "e2e", round(d["e2e"]["value"],1), "status", d["config"]["status"])
-    print("  phases", d["config"].get("phase_ms_per_step") or d["config"].get("phase_ms_per_step_rank0"))
+    print("  value", round(d["value"],1), "ms/step", round(d["ms_per_step"],1), "iters", d["detail"]["admm_iters_per_step"], "kcg", round(d["detail"]["pcg_iters_per_admm_iter"],2), "e2e", round(d["e2e"]["value"],1), "status", d["detail"]["status"])
+    print("  phases", d["detail"].get("phase_ms_per_step") or d["detail"].get("phase_ms_per_step_rank0"))
 except Exception as e:
     print("  parse failed", e)
 PY
