@@ -597,7 +597,9 @@ static void csl_autotune(b200qp_solver* sv) {
     cs.S = S_of[c]; cs.smem = (size_t)cs.S * cs.capb;
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, b200qp_csl_kernel(false), CSL_NT, cs.smem));
-    if (occ * w->stats.grid < cs.G && occ * 148 < cs.G) { ms_of[c] = 1e30f; continue; }    // cannot be co-resident
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device));
+    if (occ * sms < cs.G) { ms_of[c] = 1e30f; continue; }    // this footprint cannot keep the cooperative grid co-resident
     for (int rep = 0; rep < 2; ++rep) {
       w->x.zero(w->stream); w->z.zero(w->stream); w->y.zero(w->stream);
       KArgs a = make_args(sv);
