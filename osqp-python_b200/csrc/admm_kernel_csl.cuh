@@ -107,6 +107,55 @@ __device__ __forceinline__ void part_dot(const int* ip, const double* vp, int le
     }
   }
 }
+// Same dot products against a TAGGED vector (multi-GPU kernel): element i lives in a 16-byte {value, tag} pair that its
+// producer -- on this GPU or on a peer, over NVLink -- writes with one aligned vector store.  A gather that finds another
+// tag than the one of the current phase simply repeats: the consumer phase needs no barrier (and the producer no
+// system-scope fence) in front of it, late elements cost a few re-loads of exactly those elements.
+__device__ __forceinline__ void csl_ld_pair(const unsigned char* p, double& v, unsigned long long& e) {
+  long long bits;
+  asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(e) : "l"(p) : "memory");
+  v = __longlong_as_double(bits);
+}
+__device__ __forceinline__ void part_dot_tag(const int* ip, const double* vp, int len, int maxlen, const unsigned char* __restrict__ tagged,
+                                             unsigned long long tag, double& sa) {
+  constexpr int U = 5;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const bool uniform = __all_sync(0xffffffffu, len == maxlen);
+  int pos = 0;
+  sa = 0.0;
+  for (int j0 = 0; j0 < maxlen; j0 += U) {
+    int k[U], c[U];
+    double g[U], v[U];
+    unsigned long long e[U];
+    if (uniform) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) k[u] = (len > j0 + u) ? (j0 + u) * 32 + lane : 0;
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool act = len > j0 + u;
+        const unsigned mask = __ballot_sync(0xffffffffu, act);
+        k[u] = act ? pos + __popc(mask & lt) : 0;
+        pos += __popc(mask);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = ip[k[u]];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      g[u] = 0.0; e[u] = tag;
+      if (len > j0 + u) csl_ld_pair(tagged + (size_t)c[u] * 16, g[u], e[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = vp[k[u]];
+#pragma unroll
+    for (int u = U - 1; u >= 0; --u) {
+      while (e[u] != tag) csl_ld_pair(tagged + (size_t)c[u] * 16, g[u], e[u]);     // rare: the element is still on its way
+      sa = fma(v[u], g[u], sa);
+    }
+  }
+}
 // n-side tile, both parts at once: returns (A' part . vec2) + sign * (P part . vec1).  The first five columns of the
 // P part (usually all of it) are loaded and gathered BEFORE the A' part runs and folded in after it, chained onto
 // its sum so that ptxas cannot pull those FMAs in front of the A' gathers: one latency instead of two per tile.
@@ -802,10 +851,21 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
           double acc, dummy;
           part_dot<1, SM>(tv.i1, tv.v1, tv.len1, tv.max1, a.p, nullptr, acc, dummy);
           done();
-          if (row < a.m) { const double tv_ = rv * acc; a.w[row] = tv_; CSL_PUSH(w, row, tv_); }
+          if (row < a.m) {
+            const double tv_ = rv * acc;
+            if constexpr (DIST) {
+              if (x.tag_t) {      // {t, phase tag} to every rank's tagged copy (own included): C gathers it without a barrier
+                const unsigned long long tg = x.epoch0 + sync.epoch;
+#pragma unroll
+                for (int h = 0; h < CSL_MAXW; ++h) if (h < x.world) csl_st_slot(x.tt[h] + (size_t)row * 16, tv_, tg);
+              } else { a.w[row] = tv_; CSL_PUSH(w, row, tv_); }
+            } else {
+              a.w[row] = tv_;
+            }
+          }
         });
         if (c.cta_ns) { __syncthreads(); if (tid == 0) c.cta_ns[2 * cta] += (long long)(global_timer_ns() - tb0); }
-        CSL_BARRIER_OR_DIE();
+        if (!(DIST && x.tag_t)) CSL_BARRIER_OR_DIE();
         mark(1);
         const unsigned long long tc0 = (c.cta_ns && tid == 0) ? global_timer_ns() : 0ULL;
         // C: w = P u + sigma u + A' t ; <w, u>
@@ -816,7 +876,18 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
           const double uj = row < a.n ? __ldcg(a.p + row) : 0.0;          // in flight with the gathers
           double accP, accA, dummy;
           part_dot<1, SM>(tv.i1, tv.v1, tv.len1, tv.max1, a.p, nullptr, accP, dummy);
-          part_dot<1, SM>(tv.i2, tv.v2, tv.len2, tv.max2, a.w, nullptr, accA, dummy);
+          bool tagged = false;
+          if constexpr (DIST && SM) tagged = x.tag_t != 0;
+          if (tagged) {
+            if constexpr (DIST) {
+              const unsigned char* mine = x.tt[0];
+#pragma unroll
+              for (int h = 1; h < CSL_MAXW; ++h) if (x.rank == h) mine = x.tt[h];
+              part_dot_tag(tv.i2, tv.v2, tv.len2, tv.max2, mine, x.epoch0 + sync.epoch, accA);
+            }
+          } else {
+            part_dot<1, SM>(tv.i2, tv.v2, tv.len2, tv.max2, a.w, nullptr, accA, dummy);
+          }
           done();
           if (row < a.n) {
             const double wj = (accP + accA) + sigma * uj;

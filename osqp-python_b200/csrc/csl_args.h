@@ -47,6 +47,10 @@ struct XCsl {
   unsigned char* xslot[CSL_MAXW];            // rank h's {value, barrier number} slots [2][Gtot] x 16 B (fence-free barriers)
   double *p[CSL_MAXW], *d[CSL_MAXW], *w[CSL_MAXW], *w2[CSL_MAXW], *y[CSL_MAXW];
   int* abort_flag[CSL_MAXW];
+  // t = rho .* (A u) as a TAGGED vector: 16-byte {value, phase tag} pairs written by the producing thread into every
+  // rank's copy; the K u phase gathers it with a tag check instead of waiting at a fenced barrier after the A u phase
+  int tag_t;
+  unsigned char* tt[CSL_MAXW];               // rank h's tagged copy of t [m] x 16 B
 };
 
 }  // namespace b200qp
