@@ -413,7 +413,11 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
   // slots as they turn up -- one NVLink hop, no MEMBAR.SYS.  Having every partial also means every CTA of the job has
   // finished the phase (a CTA stores its partial after its last tile), which is all the next phase relies on: V only
   // touches the CTA's own elements of w, and overwrites u only after every gather of the old u has returned.
-  auto barrier_payload = [&](auto& v, auto k_tag, unsigned maxmask) -> bool {
+  // `site` selects the slot bank: two payload barriers that follow each other with no fenced barrier in between (C, then
+  // V in tagged-u mode) must not share slots -- a fast CTA would overwrite its slot for the second barrier while a slow
+  // one is still folding the first.  One bank per call site is enough: a site's slots are rewritten only after the other
+  // site's barrier, which every CTA enters after it has finished folding this one.
+  auto barrier_payload = [&](auto& v, auto k_tag, unsigned maxmask, int site) -> bool {
     constexpr int K = decltype(k_tag)::value;
     static_assert(K <= 2, "slot array holds two slots");
     if constexpr (!DIST) {
@@ -433,7 +437,7 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
         const bool mx = (maxmask >> tid) & 1u;
         double acc = s_red[tid * CSL_NW];
         for (int w = 1; w < CSL_NW; ++w) acc = combine(acc, s_red[tid * CSL_NW + w], mx);
-        const size_t off = ((size_t)tid * x.Gtot + x.goff + cta) * 16;
+        const size_t off = ((size_t)(site * 2 + tid) * x.Gtot + x.goff + cta) * 16;
 #pragma unroll
         for (int h = 0; h < CSL_MAXW; ++h) if (h < x.world) csl_st_slot(x.xslot[h] + off, acc, e);
       }
@@ -448,7 +452,7 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
         const bool mx = (maxmask >> k) & 1u;
         acc[k] = mx ? NEG_INF : 0.0;
         for (int cc = tid; cc < x.Gtot && ok; cc += CSL_NT) {
-          const unsigned char* sp = mine + ((size_t)k * x.Gtot + cc) * 16;
+          const unsigned char* sp = mine + ((size_t)(site * 2 + k) * x.Gtot + cc) * 16;
           double val; unsigned long long ep;
           unsigned spins = 0;
           unsigned long long t0 = 0;
@@ -489,6 +493,20 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
   // all-gather by stores: the producing thread writes its element into every peer's copy
 #define CSL_PUSH(tab, i, v) do { if constexpr (DIST) { _Pragma("unroll") for (int h_ = 0; h_ < CSL_MAXW; ++h_) if (h_ < x.world && h_ != x.rank) csl_st_sys(x.tab[h_] + (i), (v)); } } while (0)
 #define CSL_PUSH2(tab, i2, v) do { if constexpr (DIST) { _Pragma("unroll") for (int h_ = 0; h_ < CSL_MAXW; ++h_) if (h_ < x.world && h_ != x.rank) csl_st_sys2(reinterpret_cast<double2*>(x.tab[h_]) + (i2), (v)); } } while (0)
+
+  // u = M^-1 r is gathered by the A u and P u products of every rank.  Tagged mode (multi-GPU): the producer writes
+  // {u, phase tag} pairs into every rank's tagged copy (own included) and keeps the plain array for its own elements;
+  // the gathers check the tag, so the phase that follows a producer of u needs neither a fence nor the pushes to have
+  // landed.  tag_u = the barrier count at which the current u was produced (identical in every thread of the job).
+  unsigned long long tag_u = 0;
+  const bool tagged_u = DIST && x.tag_u != 0;
+#define CSL_PUT_U(i, v) do { a.p[(i)] = (v); if constexpr (DIST) { if (tagged_u) { _Pragma("unroll") for (int h_ = 0; h_ < CSL_MAXW; ++h_) if (h_ < x.world) csl_st_slot(x.tu[h_] + (size_t)(i) * 16, (v), tag_u); } else { CSL_PUSH(p, (i), (v)); } } } while (0)
+  const unsigned char* tu_mine = nullptr;
+  if constexpr (DIST) {
+    tu_mine = x.tu[0];
+#pragma unroll
+    for (int h = 1; h < CSL_MAXW; ++h) if (x.rank == h) tu_mine = x.tu[h];
+  }
 
   // ---- ring state -----------------------------------------------------------------------------------------------
   // ring_q = tiles issued / consumed so far, modulo 2S (stage = q % S, parity = q >= S); identical in every thread.
@@ -607,8 +625,7 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
     const double rj = -(px + qj) + atw;
     const double uj = a.Minv[row] * rj;
     a.r[row] = rj;
-    a.p[row] = uj;
-    CSL_PUSH(p, row, uj);
+    CSL_PUT_U(row, uj);
     v[R_RZ] += rj * uj;
     v[R_R0] = nanmax(v[R_R0], fabs(rj));
     if constexpr (FULL) {
@@ -656,6 +673,7 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
   };
   auto phase_R = [&](auto full_tag) {
     constexpr bool FULL = decltype(full_tag)::value;
+    if constexpr (DIST) tag_u = x.epoch0 + sync.epoch;
     constexpr int K = FULL ? (int)R_K : H_K;
     constexpr int TL = FULL ? (int)R_TL : H_TL;
     double v[K];
@@ -682,8 +700,7 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
           const double rj = -(px + qj) + atw;
           const double uj = mi * rj;
           a.r[row] = rj;
-          a.p[row] = uj;
-          CSL_PUSH(p, row, uj);
+          CSL_PUT_U(row, uj);
           v[R_RZ] += rj * uj;
           v[R_R0] = nanmax(v[R_R0], fabs(rj));
         }
@@ -695,6 +712,7 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
   };
   // after a rho update: px is stored, only A'w2 (and the Jacobi diagonal) change.  Off the alternating ring: plain loads.
   auto phase_R_lite = [&]() {
+    if constexpr (DIST) tag_u = x.epoch0 + sync.epoch;
     double v[H_K];
 #pragma unroll
     for (int i = 0; i < H_K; ++i) v[i] = 0.0;
@@ -849,7 +867,10 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
           const int row = tile * 32 + lane;
           const double rv = row < a.m ? __ldcg(a.rho_v + row) : 0.0;      // in flight with the gathers
           double acc, dummy;
-          part_dot<1, SM>(tv.i1, tv.v1, tv.len1, tv.max1, a.p, nullptr, acc, dummy);
+          bool tg_u = false;
+          if constexpr (DIST && SM) tg_u = tagged_u;
+          if (tg_u) part_dot_tag(tv.i1, tv.v1, tv.len1, tv.max1, tu_mine, tag_u, acc);
+          else part_dot<1, SM>(tv.i1, tv.v1, tv.len1, tv.max1, a.p, nullptr, acc, dummy);
           done();
           if (row < a.m) {
             const double tv_ = rv * acc;
@@ -875,7 +896,10 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
           const int row = tile * 32 + lane;
           const double uj = row < a.n ? __ldcg(a.p + row) : 0.0;          // in flight with the gathers
           double accP, accA, dummy;
-          part_dot<1, SM>(tv.i1, tv.v1, tv.len1, tv.max1, a.p, nullptr, accP, dummy);
+          bool tg_u = false;
+          if constexpr (DIST && SM) tg_u = tagged_u;
+          if (tg_u) part_dot_tag(tv.i1, tv.v1, tv.len1, tv.max1, tu_mine, tag_u, accP);
+          else part_dot<1, SM>(tv.i1, tv.v1, tv.len1, tv.max1, a.p, nullptr, accP, dummy);
           bool tagged = false;
           if constexpr (DIST && SM) tagged = x.tag_t != 0;
           if (tagged) {
@@ -896,7 +920,7 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
           }
         });
         if (c.cta_ns && tid == 0) c.cta_ns[2 * cta + 1] += (long long)(global_timer_ns() - tc0);
-        if (!barrier_payload(v1, std::integral_constant<int, 1>{}, 0u)) CSL_DIE();
+        if (!barrier_payload(v1, std::integral_constant<int, 1>{}, 0u, 0)) CSL_DIE();
         mark(2);
         const double delta = s_tot[0];
         const double bj = (j == 0) ? 0.0 : gam / gam_prev;
@@ -906,6 +930,7 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
         cg_total++;
         // V: p = u + b p ; s = w + b s ; d += a p ; r -= a s ; u = Minv r ; <r, u> ; |r|inf   (two elements per thread)
         double v2[2] = {0.0, 0.0};
+        const unsigned long long tag_v = DIST ? x.epoch0 + sync.epoch : 0ULL;
         {
           const int npair = (n1 - n0) >> 1;
           const double2* u2 = reinterpret_cast<const double2*>(a.p + n0);
@@ -934,7 +959,18 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
             upd(ui.x, wi.x, po.x, so.x, dold.x, ro.x, mi.x, pn.x, sn.x, dn.x, rn.x, un.x);
             upd(ui.y, wi.y, po.y, so.y, dold.y, ro.y, mi.y, pn.y, sn.y, dn.y, rn.y, un.y);
             p2[i] = pn; s2[i] = sn; d2[i] = dn; r2[i] = rn; uo2[i] = un;
-            CSL_PUSH2(p, (n0 >> 1) + i, un);
+            if constexpr (DIST) {
+              if (tagged_u) {
+#pragma unroll
+                for (int h_ = 0; h_ < CSL_MAXW; ++h_)
+                  if (h_ < x.world) {
+                    csl_st_slot(x.tu[h_] + (size_t)(n0 + 2 * i) * 16, un.x, tag_v);
+                    csl_st_slot(x.tu[h_] + (size_t)(n0 + 2 * i + 1) * 16, un.y, tag_v);
+                  }
+              } else {
+                CSL_PUSH2(p, (n0 >> 1) + i, un);
+              }
+            }
           }
           if (((n1 - n0) & 1) && tid == 0) {
             const int i = n1 - 1;
@@ -942,13 +978,26 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
             upd(__ldcg(a.p + i), __ldcg(a.kp + i), j > 0 ? c.ps[i] : 0.0, j > 0 ? c.ss[i] : 0.0, j > 0 ? a.d[i] : 0.0, a.r[i],
                 a.Minv[i], pn, sn, dn, rn, un);
             c.ps[i] = pn; c.ss[i] = sn; a.d[i] = dn; a.r[i] = rn; a.p[i] = un;
-            CSL_PUSH(p, i, un);
+            if constexpr (DIST) {
+              if (tagged_u) {
+#pragma unroll
+                for (int h_ = 0; h_ < CSL_MAXW; ++h_) if (h_ < x.world) csl_st_slot(x.tu[h_] + (size_t)i * 16, un, tag_v);
+              } else {
+                CSL_PUSH(p, i, un);
+              }
+            }
           }
         }
         have_d = true;
-        reduce_store(v2, std::integral_constant<int, 2>{}, 2u);
-        CSL_BARRIER_OR_DIE();
-        reduce_load(std::integral_constant<int, 2>{}, 2u);
+        if constexpr (DIST) tag_u = tag_v;          // the gathers of the next A u / P u expect this phase's u
+        if (tagged_u) {
+          // nothing of this phase has to have landed anywhere when the next one starts: fence-free payload barrier
+          if (!barrier_payload(v2, std::integral_constant<int, 2>{}, 2u, 1)) CSL_DIE();
+        } else {
+          reduce_store(v2, std::integral_constant<int, 2>{}, 2u);
+          CSL_BARRIER_OR_DIE();
+          reduce_load(std::integral_constant<int, 2>{}, 2u);
+        }
         mark(3);
         gam_prev = gam;
         gam = s_tot[0];
@@ -1069,6 +1118,7 @@ admm_kernel_csl(const __grid_constant__ KArgs a, const __grid_constant__ CArgs c
 #undef CSL_BARRIER_OR_DIE
 #undef CSL_PUSH
 #undef CSL_PUSH2
+#undef CSL_PUT_U
 }
 
 }  // namespace b200qp

@@ -220,7 +220,7 @@ struct Work {
 // shared-region layout of a multi-GPU rank (same offsets on every rank): control block, arrival flags, barrier
 // payload, then the five gathered vectors -- w, w2, y (length m) and p, d (length n)
 struct RegionLayout {
-  size_t ctrl, flags, payload, arrive, hdr, xbank, xslot, wf, w2f, yf, p, d, tt, total;
+  size_t ctrl, flags, payload, arrive, hdr, xbank, xslot, wf, w2f, yf, p, d, tt, tu, total;
   RegionLayout(size_t n, size_t m) {
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t o = 0;
@@ -230,10 +230,11 @@ struct RegionLayout {
     arrive = o; o = al(o + (size_t)MAXW * CSL_GMAX * sizeof(unsigned long long));   // tile kernel: one flag per CTA of the job
     hdr = o; o = al(o + 4 * sizeof(int));                        // {G of this rank, uses the tile kernel}
     xbank = o; o = al(o + (size_t)2 * KMAX * MAXW * CSL_GMAX * sizeof(double));
-    xslot = o; o = al(o + (size_t)2 * MAXW * CSL_GMAX * 16);
+    xslot = o; o = al(o + (size_t)2 * 2 * MAXW * CSL_GMAX * 16);   // two call sites x two slots
     const size_t vn = al(n * sizeof(double)), vm = al(std::max<size_t>(m, 1) * sizeof(double));
     wf = o; o += vm; w2f = o; o += vm; yf = o; o += vm; p = o; o += vn; d = o; o += vn;
     tt = o; o += 2 * vm;                                          // tile kernel: tagged copy of t, 16 bytes per row
+    tu = o; o += 2 * vn;                                          // and of u, 16 bytes per variable
     total = o;
   }
 };
@@ -458,9 +459,12 @@ XCsl make_xcsl(Work* w) {
     x.w[h] = (double*)(b + L.wf); x.w2[h] = (double*)(b + L.w2f); x.y[h] = (double*)(b + L.yf);
     x.abort_flag[h] = &((Ctrl*)(b + L.ctrl))->abort;
     x.tt[h] = (unsigned char*)(b + L.tt);
+    x.tu[h] = (unsigned char*)(b + L.tu);
   }
   x.tag_t = 1;
   if (const char* e = std::getenv("B200QP_DIST_TAGGED_T")) x.tag_t = std::atoi(e) ? 1 : 0;
+  x.tag_u = 0;
+  if (const char* e = std::getenv("B200QP_DIST_TAGGED_U")) x.tag_u = std::atoi(e) ? 1 : 0;
   return x;
 }
 

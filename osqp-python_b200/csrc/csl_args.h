@@ -44,13 +44,16 @@ struct XCsl {
   unsigned long long epoch0;                 // cross-GPU barriers completed by earlier launches (counters are never reset)
   unsigned long long* xflag[CSL_MAXW];       // rank h's arrival flags, one per CTA of the job [Gtot]
   double* xbank[CSL_MAXW];                   // rank h's reduction banks [2][KMAX][Gtot]
-  unsigned char* xslot[CSL_MAXW];            // rank h's {value, barrier number} slots [2][Gtot] x 16 B (fence-free barriers)
+  unsigned char* xslot[CSL_MAXW];            // rank h's {value, barrier number} slots [2 sites][2][Gtot] x 16 B (fence-free barriers)
   double *p[CSL_MAXW], *d[CSL_MAXW], *w[CSL_MAXW], *w2[CSL_MAXW], *y[CSL_MAXW];
   int* abort_flag[CSL_MAXW];
   // t = rho .* (A u) as a TAGGED vector: 16-byte {value, phase tag} pairs written by the producing thread into every
   // rank's copy; the K u phase gathers it with a tag check instead of waiting at a fenced barrier after the A u phase
   int tag_t;
   unsigned char* tt[CSL_MAXW];               // rank h's tagged copy of t [m] x 16 B
+  // the same for u = M^-1 r (gathered by the A u and P u products): no fenced barrier after the phases that produce it
+  int tag_u;
+  unsigned char* tu[CSL_MAXW];               // rank h's tagged copy of u [n] x 16 B
 };
 
 }  // namespace b200qp
