@@ -309,23 +309,33 @@ def test_c2_lasso_full_size_properties():
 
 def test_c3_svm_full_size_warm_start_polish():
     """BASELINE config 3 at full size: SVM QP n = 5e4, m = 1e5 (n_feat 1e4, n_data 4e4, +2e4 box rows), adaptive rho,
-    then perturbed q + warm start + polish."""
+    then perturbed q + warm start + polish.  At eps 1e-5 the active set is identified and the polish must SUCCEED, cold
+    and warm-started, leaving a point at KKT residuals ~1e-12 (a factorisation-class answer from an iterative engine);
+    at the default eps 1e-3 the reference algorithm's own acceptance test may reject the guess (-1), as it does on the
+    reduced instances of tests/test_gpu_parity2.py::test_polish_status_follows_the_reference_algorithm."""
     import osqp
     from b200qp import problems
     P, q, A, l, u = problems.svm_qp(10_000, 40_000, density=0.01, seed=2, box_rows=20_000)
     assert P.shape[0] == 50_000 and A.shape[0] == 100_000
     prob = osqp.OSQP()
-    prob.setup(P, q, A, l, u, verbose=False, adaptive_rho=True, polishing=True, max_iter=10000)
+    prob.setup(P, q, A, l, u, verbose=False, adaptive_rho=True, polishing=True, max_iter=20000, eps_abs=1e-5, eps_rel=1e-5)
     r1 = prob.solve()
-    assert r1.info.status == "solved"
+    assert r1.info.status == "solved" and r1.info.status_polish == 1
     rep = problems.kkt_report(P, q, A, l, u, r1.x, r1.y)
-    assert rep["prim"] <= 1e-2 and rep["dual"] <= 1e-2
+    assert rep["prim"] <= 1e-9 and rep["dual"] <= 1e-9
     q2 = q * (1 + 0.01 * np.cos(np.arange(len(q))))
     prob.update(q=q2)
     prob.warm_start(x=r1.x, y=r1.y)
     r2 = prob.solve()
     assert r2.info.status == "solved" and r2.info.iter <= r1.info.iter
-    assert r2.info.status_polish in (1, -1)
+    assert r2.info.status_polish == 1
     rep2 = problems.kkt_report(P, q2, A, l, u, r2.x, r2.y)
-    assert rep2["prim"] <= 1e-2 and rep2["dual"] <= 1e-2
-    print("C3 full:", r1.info.iter, r2.info.iter, r1.info.status_polish, r2.info.status_polish, rep, rep2)
+    assert rep2["prim"] <= 1e-9 and rep2["dual"] <= 1e-9
+    # default tolerances: still a solve within the loose bounds, polish status whatever the acceptance test says
+    loose = osqp.OSQP()
+    loose.setup(P, q, A, l, u, verbose=False, adaptive_rho=True, polishing=True, max_iter=10000)
+    r3 = loose.solve()
+    assert r3.info.status == "solved" and r3.info.status_polish in (1, -1)
+    rep3 = problems.kkt_report(P, q, A, l, u, r3.x, r3.y)
+    assert rep3["prim"] <= 1e-2 and rep3["dual"] <= 1e-2
+    print("C3 full:", r1.info.iter, r2.info.iter, r1.info.status_polish, r2.info.status_polish, r3.info.status_polish, rep, rep2)
