@@ -35,6 +35,12 @@ def prepare(verbose=True):
         shutil.copy(f, os.path.join(pkg, "tests"))
     for f in glob.glob(os.path.join(ROOT, "tests", "golden", "ref_solutions", "*.npz")):
         shutil.copy(f, os.path.join(pkg, "tests", "solutions"))
+    # the reference's in-scope example scripts, copied at build time like the facade, never committed
+    ex = os.path.join(WORK, "examples")
+    shutil.rmtree(ex, ignore_errors=True)
+    os.makedirs(ex)
+    for f in ("basic_usage.py", "update_vectors.py", "update_matrices.py", "exception_handling.py"):
+        shutil.copy(os.path.join(REF, "examples", f), os.path.join(ex, f))
     # Option A: the reference's unmodified binding source over the shim headers
     optA = os.path.join(WORK, "optionA")
     os.makedirs(optA, exist_ok=True)
