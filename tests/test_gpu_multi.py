@@ -110,3 +110,36 @@ def test_group_infeasible_and_unconstrained():
     r = LocalGroup(case["P"], case["q"], case["A"], case["l"], case["u"], [0, 0], **st).solve()[0]
     assert r.info.status == "solved"
     np.testing.assert_allclose(r.x, case["expect"]["ref_x_val"], rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("fmt,kind", [("tiles", 3), ("csr", 2)])
+def test_group_kernel_selection_and_csr_fallback(fmt, kind, monkeypatch):
+    """Both multi-GPU kernels behind the same driver: the tile kernel (admm_kernel_csl<true>, default) and the CSR
+    fallback (admm_kernel_dist; B200QP_DIST_FORMAT=csr, or matrices the tiles cannot hold) -- same solution, the
+    kernel in use reported by stats().  With the tile kernel every rank holds all of y at exit (row range [0, m))."""
+    import osqp
+    from b200qp import problems
+    from b200qp.multigpu import LocalGroup
+    if fmt == "csr":
+        monkeypatch.setenv("B200QP_DIST_FORMAT", "csr")
+    P, q, A, l, u = problems.random_qp(6000, 8000, nnz_per_row=8, seed=11, eq_frac=0.1)
+    kw = dict(verbose=False, eps_abs=1e-7, eps_rel=1e-7, max_iter=20000)
+    prob = osqp.OSQP()
+    prob.setup(P, q, A, l, u, **kw)
+    single = prob.solve()
+    assert single.info.status == "solved"
+    grp = LocalGroup(P, q, A, l, u, [0, 0, 0], **kw)
+    results = grp.solve()
+    assert all(st["kernel_kind"] == kind for st in grp.stats())
+    ranges = [s.dist_row_range() for s in grp.solvers]
+    if kind == 3:
+        assert all(tuple(rg) == (0, A.shape[0]) for rg in ranges)
+    else:
+        assert ranges[0][0] == 0 and ranges[-1][1] == A.shape[0] and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    r0 = results[0]
+    for r in results:
+        assert r.info.status == "solved" and r.info.iter == r0.info.iter
+        np.testing.assert_array_equal(r.x, r0.x)
+        np.testing.assert_array_equal(r.y, r0.y)
+    assert abs(r0.info.iter - single.info.iter) <= max(25, 0.1 * single.info.iter)
+    assert _rel(r0.x, single.x) <= 1e-5 and _rel(r0.y, single.y) <= 1e-4
