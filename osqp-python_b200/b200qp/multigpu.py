@@ -203,7 +203,7 @@ def bench(args, rank, world, local, B):
                          "peak_source": peak_src, "traffic": None,
                          "note": "per-GPU share of the single-GPU algorithmic byte model / max-over-ranks device time"},
             "e2e": {"value": iters / (wall_ms * 1e-3), "unit": B.UNIT, "h2d_bytes_per_step": 8 * n * world,
-                    "d2h_bytes_per_step": (16 * (n + m) + 128) * world, "ms_per_step": wall_ms / args.steps,
+                    "d2h_bytes_per_step": (8 * (n + m) + 200) * world, "ms_per_step": wall_ms / args.steps,
                     "api": "DistSolver.update(q=host) + solve() -> x, y on every rank's host (complete on every rank: no gather)"},
             "gpu_launches": args.steps * 6 * world,
             "clocks": clocks,
